@@ -1,0 +1,224 @@
+"""ctypes bindings for the two parity checkers.  TEST INFRASTRUCTURE ONLY.
+
+* ``Checker("orc")`` -> oracle/libbn254oracle.so, the plain-C restatement
+  (oracle/bn254_oracle.c).
+* ``Checker("ref")`` -> oracle/_ref/libffref.so, the UNMODIFIED reference libff
+  sources compiled in place by oracle/Makefile (wrapper: oracle/ref_wrap.cpp).
+
+Both export the same functions (prefix ``orc_`` / ``ref_``); arrays are numpy
+``uint64`` little-endian Montgomery limbs: Fr/Fq ``(n, 4)``, Fq2 ``(n, 8)``,
+G1 ``(n, 12)`` Jacobian X|Y|Z, G2 ``(n, 24)``.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORC_PATH = os.path.join(HERE, "libbn254oracle.so")
+REF_PATH = os.path.join(HERE, "_ref", "libffref.so")
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+
+Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+MONT_R = 1 << 256
+
+
+def build_oracle() -> str:
+    """Compile the C restatement (gcc only; works on the GPU box too)."""
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    return ORC_PATH
+
+
+def build_ref() -> str | None:
+    """Compile oracle/_ref from /root/reference when it is present."""
+    subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+    return REF_PATH if os.path.exists(REF_PATH) else None
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_u64p)
+
+
+def _c(a, width=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if width is not None:
+        a = a.reshape(-1, width)
+    return a
+
+
+class Checker:
+    """Uniform view over the restatement ("orc") and the compiled reference ("ref")."""
+
+    def __init__(self, kind: str = "orc"):
+        assert kind in ("orc", "ref")
+        self.kind = kind
+        if kind == "orc":
+            if not os.path.exists(ORC_PATH) or os.path.getmtime(ORC_PATH) < os.path.getmtime(
+                os.path.join(HERE, "bn254_oracle.c")
+            ):
+                build_oracle()
+            path = ORC_PATH
+        else:
+            if not os.path.exists(REF_PATH):
+                if os.path.isdir("/root/reference"):
+                    build_ref()
+            if not os.path.exists(REF_PATH):
+                raise FileNotFoundError("oracle/_ref/libffref.so not built (needs /root/reference)")
+            path = REF_PATH
+        self.lib = ctypes.CDLL(path)
+        self.p = kind + "_"
+        self.curve_arg = kind == "ref"
+        if kind == "ref":
+            self.lib.ref_init()
+        for name in ("exp_window_size_g1", "exp_window_size_g2"):
+            f = getattr(self.lib, self.p + name)
+            f.restype = ctypes.c_size_t
+            f.argtypes = [ctypes.c_size_t]
+
+    @staticmethod
+    def available(kind: str) -> bool:
+        if kind == "orc":
+            return True
+        return os.path.exists(REF_PATH) or os.path.isdir("/root/reference")
+
+    # -- helpers ---------------------------------------------------------
+    def _call(self, name, *args):
+        rc = getattr(self.lib, self.p + name)(*args)
+        if rc != 0:
+            raise RuntimeError(f"{self.p}{name} returned {rc}")
+
+    def max_threads(self) -> int:
+        return int(getattr(self.lib, self.p + "max_threads")())
+
+    # -- MSM ---------------------------------------------------------------
+    def msm(self, group, bases, scalars, chunks=1, variant=0, normalise=True, curve=0):
+        L = 12 if group == "g1" else 24
+        bases = _c(bases, L)
+        scalars = _c(scalars, 4)
+        n = bases.shape[0]
+        assert scalars.shape[0] == n
+        out = np.zeros(L, dtype=np.uint64)
+        args = [_ptr(bases), _ptr(scalars), ctypes.c_size_t(n), ctypes.c_size_t(chunks), int(variant),
+                int(bool(normalise)), _ptr(out)]
+        if self.curve_arg:
+            args = [int(curve)] + args
+        self._call("msm_" + group, *args)
+        return out
+
+    # -- fixed-base batch_exp ---------------------------------------------
+    def batch_exp(self, group, base, scalars, coeff=None, window=0, normalise=True, curve=0):
+        L = 12 if group == "g1" else 24
+        base = _c(base, L)
+        scalars = _c(scalars, 4)
+        n = scalars.shape[0]
+        coeff = None if coeff is None else _c(coeff, 4)
+        out = np.zeros((n, L), dtype=np.uint64)
+        args = [_ptr(base), _ptr(scalars), ctypes.c_size_t(n), _ptr(coeff), ctypes.c_size_t(window),
+                int(bool(normalise)), _ptr(out)]
+        if self.curve_arg:
+            args = [int(curve)] + args
+        self._call("batch_exp_" + group, *args)
+        return out
+
+    def exp_window_size(self, group, n) -> int:
+        return int(getattr(self.lib, self.p + "exp_window_size_" + group)(n))
+
+    def batch_to_special(self, group, pts, curve=0):
+        L = 12 if group == "g1" else 24
+        pts = _c(pts, L).copy()
+        args = [_ptr(pts), ctypes.c_size_t(pts.shape[0])]
+        if self.curve_arg:
+            args = [int(curve)] + args
+        self._call("batch_to_special_" + group, *args)
+        return pts
+
+    # -- element-wise group / field ops ------------------------------------
+    def group_op(self, group, op, a, b=None, curve=0):
+        L = 12 if group == "g1" else 24
+        a = _c(a, L)
+        b = None if b is None else _c(b, L)
+        out = np.zeros_like(a)
+        args = [int(op), _ptr(a), _ptr(b), ctypes.c_size_t(a.shape[0]), _ptr(out)]
+        if self.curve_arg:
+            args = [int(curve)] + args
+        self._call(group + "_op", *args)
+        return out
+
+    def scalar_mul(self, group, base, scalars, stride_base=False, normalise=True):
+        L = 12 if group == "g1" else 24
+        base = _c(base, L)
+        scalars = _c(scalars, 4)
+        n = scalars.shape[0]
+        out = np.zeros((n, L), dtype=np.uint64)
+        self._call("scalar_mul_" + group, _ptr(base), _ptr(scalars), ctypes.c_size_t(n), int(bool(stride_base)),
+                   int(bool(normalise)), _ptr(out))
+        return out
+
+    def field_op(self, field, op, a, b=None):
+        W = {"fq": 4, "fr": 4, "fq2": 8}[field]
+        a = _c(a, W)
+        b = None if b is None else _c(b, W)
+        out = np.zeros_like(a)
+        self._call(field + "_op", int(op), _ptr(a), _ptr(b), ctypes.c_size_t(a.shape[0]), _ptr(out))
+        return out
+
+    def fr_from_bigint(self, a):
+        a = _c(a, 4)
+        out = np.zeros_like(a)
+        self._call("fr_from_bigint", _ptr(a), ctypes.c_size_t(a.shape[0]), _ptr(out))
+        return out
+
+    def fr_as_bigint(self, a):
+        a = _c(a, 4)
+        out = np.zeros_like(a)
+        self._call("fr_as_bigint", _ptr(a), ctypes.c_size_t(a.shape[0]), _ptr(out))
+        return out
+
+    def fq_from_bigint(self, a):
+        a = _c(a, 4)
+        out = np.zeros_like(a)
+        self._call("fq_from_bigint", _ptr(a), ctypes.c_size_t(a.shape[0]), _ptr(out))
+        return out
+
+    def sha512_rng_fr(self, idx0, n):
+        out = np.zeros((n, 4), dtype=np.uint64)
+        self._call("sha512_rng_fr", ctypes.c_uint64(idx0), ctypes.c_size_t(n), _ptr(out))
+        return out
+
+    def one(self, group):
+        L = 12 if group == "g1" else 24
+        out = np.zeros(L, dtype=np.uint64)
+        self._call(group + "_one", _ptr(out))
+        return out
+
+
+# -- pure-python integer helpers shared by tests / bench (no group arithmetic) --
+def int_to_limbs(x: int, n: int = 4) -> np.ndarray:
+    return np.array([(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)], dtype=np.uint64)
+
+
+def limbs_to_int(a) -> int:
+    a = np.asarray(a, dtype=np.uint64).reshape(-1)
+    return sum(int(v) << (64 * i) for i, v in enumerate(a))
+
+
+def ints_to_mont(xs, mod: int) -> np.ndarray:
+    """Standard integers -> (n, 4) Montgomery limbs for the field of the given modulus."""
+    out = np.zeros((len(xs), 4), dtype=np.uint64)
+    for i, x in enumerate(xs):
+        out[i] = int_to_limbs((x % mod) * MONT_R % mod)
+    return out
+
+
+def mont_to_ints(a, mod: int):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1, 4)
+    rinv = pow(MONT_R, -1, mod)
+    return [limbs_to_int(row) * rinv % mod for row in a]

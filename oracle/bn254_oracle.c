@@ -1,0 +1,527 @@
+/* bn254_oracle.c — plain-C CPU restatement of the reference's MSM / batch_exp
+ * hot path over BN254 (alt_bn128 / bn128).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library, and
+ * only as the checker.  The product (legosnark_b200/libb200msm.so) never links
+ * or calls it and has no CPU fallback.
+ *
+ * Parity status: PINNED against the unmodified reference sources compiled in
+ * place (oracle/_ref/libffref.so, recipe in oracle/Makefile) and against the
+ * committed fixtures under tests/golden/ generated from that build.
+ *
+ * Abbreviations: LFF = /root/reference/depends/libsnark/depends/libff/libff.
+ * Representation: 4 x u64 little-endian limbs, Montgomery form, R = 2^256
+ * (LFF/algebra/fields/fp.hpp:42, bigint.hpp:35).
+ */
+#include "bn254_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+
+/* ------------------------------------------------------------------ */
+/* bigint<4> helpers: LFF/algebra/fields/bigint.tcc:103-130,150-164    */
+/* ------------------------------------------------------------------ */
+static size_t bigint_num_bits(const uint64_t a[4])
+{
+    for (int i = 3; i >= 0; --i) {
+        if (a[i] != 0) return (size_t)(64 * (i + 1) - __builtin_clzll(a[i]));
+    }
+    return 0;
+}
+
+static int bigint_test_bit(const uint64_t a[4], size_t bitno)
+{
+    if (bitno >= 256) return 0;
+    return (int)((a[bitno >> 6] >> (bitno & 63)) & 1);
+}
+
+/* libff::log2 = ceil(log2(n)), LFF/common/utils.cpp:32-45 */
+static size_t orc_log2(size_t n)
+{
+    size_t r = ((n & (n - 1)) == 0 ? 0 : 1);
+    while (n > 1) {
+        n >>= 1;
+        r++;
+    }
+    return r;
+}
+
+/* ------------------------------------------------------------------ */
+/* Fp_model<4, p>: LFF/algebra/fields/fp.tcc                            */
+/* ------------------------------------------------------------------ */
+typedef struct { uint64_t l[4]; } fp_t;
+typedef struct {
+    uint64_t m[4]; /* modulus */
+    uint64_t inv;  /* -p^{-1} mod 2^64 (alt_bn128_init.cpp:48,74) */
+    fp_t one;      /* R mod p */
+    fp_t r2;       /* R^2 mod p (Rsquared, alt_bn128_init.cpp:46,72) */
+} fpctx_t;
+
+/* q, r: alt_bn128_init.cpp:40,66 ; bn128_init.cpp:38,63 (identical values) */
+static const fpctx_t FQ = {
+    {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
+    0x87d20782e4866389ULL,
+    {{0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL}},
+    {{0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL}},
+};
+static const fpctx_t FR = {
+    {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
+    0xc2e1f593efffffffULL,
+    {{0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL}},
+    {{0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL}},
+};
+
+static int limbs_geq(const uint64_t a[4], const uint64_t b[4])
+{
+    for (int i = 3; i >= 0; --i) {
+        if (a[i] > b[i]) return 1;
+        if (a[i] < b[i]) return 0;
+    }
+    return 1;
+}
+
+static uint64_t limbs_sub(uint64_t o[4], const uint64_t a[4], const uint64_t b[4])
+{
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a[i] - b[i] - borrow;
+        o[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+    return borrow;
+}
+
+static uint64_t limbs_add(uint64_t o[4], const uint64_t a[4], const uint64_t b[4])
+{
+    uint64_t carry = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 s = (u128)a[i] + b[i] + carry;
+        o[i] = (uint64_t)s;
+        carry = (uint64_t)(s >> 64);
+    }
+    return carry;
+}
+
+static int fp_is_zero_raw(const uint64_t a[4]) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
+
+/* mul_reduce: Montgomery product a*b*R^-1 mod p with one final conditional
+ * subtraction (HAC 14.36 as in fp.tcc:161-186; CIOS ordering gives the same value). */
+static void mont_mul_raw(uint64_t o[4], const uint64_t a[4], const uint64_t b[4], const fpctx_t *c)
+{
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u128 carry = 0;
+        for (int j = 0; j < 4; j++) {
+            u128 s = (u128)a[j] * b[i] + t[j] + carry;
+            t[j] = (uint64_t)s;
+            carry = s >> 64;
+        }
+        u128 s = (u128)t[4] + carry;
+        t[4] = (uint64_t)s;
+        t[5] = (uint64_t)(s >> 64);
+        uint64_t m = t[0] * c->inv;
+        carry = ((u128)m * c->m[0] + t[0]) >> 64;
+        for (int j = 1; j < 4; j++) {
+            s = (u128)m * c->m[j] + t[j] + carry;
+            t[j - 1] = (uint64_t)s;
+            carry = s >> 64;
+        }
+        s = (u128)t[4] + carry;
+        t[3] = (uint64_t)s;
+        t[4] = t[5] + (uint64_t)(s >> 64);
+    }
+    if (t[4] || limbs_geq(t, c->m)) limbs_sub(t, t, c->m);
+    memcpy(o, t, 32);
+}
+
+static void fp_mul(fp_t *o, const fp_t *a, const fp_t *b, const fpctx_t *c) { mont_mul_raw(o->l, a->l, b->l, c); }
+
+/* operator+= : fp.tcc:309-420 (add, then subtract p if carry or >= p) */
+static void fp_add(fp_t *o, const fp_t *a, const fp_t *b, const fpctx_t *c)
+{
+    uint64_t t[4];
+    uint64_t carry = limbs_add(t, a->l, b->l);
+    if (carry || limbs_geq(t, c->m)) limbs_sub(t, t, c->m);
+    memcpy(o->l, t, 32);
+}
+
+/* operator-= : fp.tcc:422-510 (if a < b add p first) */
+static void fp_sub(fp_t *o, const fp_t *a, const fp_t *b, const fpctx_t *c)
+{
+    uint64_t t[4];
+    uint64_t borrow = limbs_sub(t, a->l, b->l);
+    if (borrow) limbs_add(t, t, c->m);
+    memcpy(o->l, t, 32);
+}
+
+/* operator-() : fp.tcc:551-567 (zero stays zero, else p - a) */
+static void fp_neg(fp_t *o, const fp_t *a, const fpctx_t *c)
+{
+    if (fp_is_zero_raw(a->l)) { *o = *a; return; }
+    limbs_sub(o->l, c->m, a->l);
+}
+
+/* as_bigint(): mul_reduce by the integer 1, fp.tcc:227-238 */
+static void fp_as_bigint(uint64_t o[4], const uint64_t a_mont[4], const fpctx_t *c)
+{
+    const uint64_t one[4] = {1, 0, 0, 0};
+    mont_mul_raw(o, a_mont, one, c);
+}
+
+/* Fp_model(bigint): mul_reduce(Rsquared), fp.tcc:189-194 */
+static void fp_from_bigint(fp_t *o, const uint64_t a[4], const fpctx_t *c) { mont_mul_raw(o->l, a, c->r2.l, c); }
+
+/* inverse(): the reference runs mpn_gcdext then multiplies by R^3 (fp.tcc:641-685).
+ * The inverse of a field element is unique, so a^(p-2) (square-and-multiply
+ * over the Montgomery representation) returns the identical limbs. */
+static void fp_inv(fp_t *o, const fp_t *a, const fpctx_t *c)
+{
+    uint64_t e[4];
+    const uint64_t two[4] = {2, 0, 0, 0};
+    limbs_sub(e, c->m, two);
+    fp_t r = c->one, base = *a;
+    for (int i = 0; i < 256; i++) {
+        if ((e[i >> 6] >> (i & 63)) & 1) fp_mul(&r, &r, &base, c);
+        fp_mul(&base, &base, &base, c);
+    }
+    *o = r;
+}
+
+/* ---- Fq wrappers with the name shape bn254_group.inc expects ---- */
+typedef fp_t fq_t;
+static void fq_mul(fq_t *o, const fq_t *a, const fq_t *b) { fp_mul(o, a, b, &FQ); }
+static void fq_sqr(fq_t *o, const fq_t *a) { fp_mul(o, a, a, &FQ); }
+static void fq_add(fq_t *o, const fq_t *a, const fq_t *b) { fp_add(o, a, b, &FQ); }
+static void fq_sub(fq_t *o, const fq_t *a, const fq_t *b) { fp_sub(o, a, b, &FQ); }
+static void fq_neg(fq_t *o, const fq_t *a) { fp_neg(o, a, &FQ); }
+static void fq_inv(fq_t *o, const fq_t *a) { fp_inv(o, a, &FQ); }
+static int fq_is_zero(const fq_t *a) { return fp_is_zero_raw(a->l); }
+static int fq_eq(const fq_t *a, const fq_t *b) { return memcmp(a->l, b->l, 32) == 0; }
+static void fq_set_zero(fq_t *a) { memset(a->l, 0, 32); }
+static void fq_set_one(fq_t *a) { *a = FQ.one; }
+
+/* ------------------------------------------------------------------ */
+/* Fp2_model: LFF/algebra/fields/fp2.tcc, non_residue = -1              */
+/* (alt_bn128_init.cpp:95), layout c0,c1 (fp2.hpp:49)                   */
+/* ------------------------------------------------------------------ */
+typedef struct { fq_t c0, c1; } fq2_t;
+
+/* Karatsuba, fp2.tcc:72-84 */
+static void fq2_mul(fq2_t *o, const fq2_t *x, const fq2_t *y)
+{
+    fq_t aA, bB, s, t, c1;
+    fq_mul(&aA, &x->c0, &y->c0);
+    fq_mul(&bB, &x->c1, &y->c1);
+    fq_add(&s, &x->c0, &x->c1);
+    fq_add(&t, &y->c0, &y->c1);
+    fq_mul(&c1, &s, &t);
+    fq_sub(&c1, &c1, &aA);
+    fq_sub(&c1, &c1, &bB);
+    fq_sub(&o->c0, &aA, &bB); /* aA + non_residue*bB */
+    o->c1 = c1;
+}
+
+/* squared_complex, fp2.tcc:111-120 */
+static void fq2_sqr(fq2_t *o, const fq2_t *x)
+{
+    fq_t ab, s, d, c0;
+    fq_mul(&ab, &x->c0, &x->c1);
+    fq_add(&s, &x->c0, &x->c1);
+    fq_sub(&d, &x->c0, &x->c1); /* a + non_residue*b */
+    fq_mul(&c0, &s, &d);        /* (a+b)(a-b) - ab - (-ab) = (a+b)(a-b) */
+    o->c0 = c0;
+    fq_add(&o->c1, &ab, &ab);
+}
+
+static void fq2_add(fq2_t *o, const fq2_t *a, const fq2_t *b) { fq_add(&o->c0, &a->c0, &b->c0); fq_add(&o->c1, &a->c1, &b->c1); }
+static void fq2_sub(fq2_t *o, const fq2_t *a, const fq2_t *b) { fq_sub(&o->c0, &a->c0, &b->c0); fq_sub(&o->c1, &a->c1, &b->c1); }
+static void fq2_neg(fq2_t *o, const fq2_t *a) { fq_neg(&o->c0, &a->c0); fq_neg(&o->c1, &a->c1); }
+
+/* inverse, fp2.tcc:122-136 */
+static void fq2_inv(fq2_t *o, const fq2_t *x)
+{
+    fq_t t0, t1, t2, t3;
+    fq_sqr(&t0, &x->c0);
+    fq_sqr(&t1, &x->c1);
+    fq_add(&t2, &t0, &t1); /* t0 - non_residue*t1 */
+    fq_inv(&t3, &t2);
+    fq_mul(&o->c0, &x->c0, &t3);
+    fq_mul(&t0, &x->c1, &t3);
+    fq_neg(&o->c1, &t0);
+}
+static int fq2_is_zero(const fq2_t *a) { return fq_is_zero(&a->c0) && fq_is_zero(&a->c1); }
+static int fq2_eq(const fq2_t *a, const fq2_t *b) { return fq_eq(&a->c0, &b->c0) && fq_eq(&a->c1, &b->c1); }
+static void fq2_set_zero(fq2_t *a) { fq_set_zero(&a->c0); fq_set_zero(&a->c1); }
+static void fq2_set_one(fq2_t *a) { fq_set_one(&a->c0); fq_set_zero(&a->c1); }
+
+/* ------------------------------------------------------------------ */
+/* get_exp_window_size, multiexp.tcc:509-545; tables:                   */
+/* alt_bn128_init.cpp:157-201 (G1), :220-264 (G2)                       */
+/* ------------------------------------------------------------------ */
+static const size_t G1_WTAB[22] = {1, 5, 11, 32, 55, 162, 360, 815, 2373, 6978, 7122, 0, 57818, 0, 169679,
+                                   439759, 936073, 0, 4666555, 7580404, 0, 34552892};
+static const size_t G2_WTAB[22] = {1, 5, 10, 25, 59, 154, 334, 743, 2034, 4988, 8888, 26271, 39768, 106276,
+                                   141703, 462423, 926872, 0, 4873049, 5706708, 0, 31673815};
+
+static size_t orc_exp_window_size(const size_t *tab, size_t len, size_t num_scalars)
+{
+    size_t window = 1;
+    for (long i = (long)len - 1; i >= 0; --i) {
+        if (tab[i] != 0 && num_scalars >= tab[i]) {
+            window = (size_t)i + 1;
+            break;
+        }
+    }
+    return window;
+}
+
+/* ------------------------------------------------------------------ */
+/* group law + multiexp, instantiated for G1 (Fq) and G2 (Fq2)          */
+/* ------------------------------------------------------------------ */
+#define GP g1
+#define FE fq
+#include "bn254_group.inc"
+#undef GP
+#undef FE
+
+#define GP g2
+#define FE fq2
+#include "bn254_group.inc"
+#undef GP
+#undef FE
+
+/* ------------------------------------------------------------------ */
+/* SHA-512 (FIPS 180-4) for SHA512_rng, LFF/common/rng.tcc:26-72        */
+/* ------------------------------------------------------------------ */
+static const uint64_t K512[80] = {
+    0x428a2f98d728ae22ULL, 0x7137449123ef65cdULL, 0xb5c0fbcfec4d3b2fULL, 0xe9b5dba58189dbbcULL, 0x3956c25bf348b538ULL,
+    0x59f111f1b605d019ULL, 0x923f82a4af194f9bULL, 0xab1c5ed5da6d8118ULL, 0xd807aa98a3030242ULL, 0x12835b0145706fbeULL,
+    0x243185be4ee4b28cULL, 0x550c7dc3d5ffb4e2ULL, 0x72be5d74f27b896fULL, 0x80deb1fe3b1696b1ULL, 0x9bdc06a725c71235ULL,
+    0xc19bf174cf692694ULL, 0xe49b69c19ef14ad2ULL, 0xefbe4786384f25e3ULL, 0x0fc19dc68b8cd5b5ULL, 0x240ca1cc77ac9c65ULL,
+    0x2de92c6f592b0275ULL, 0x4a7484aa6ea6e483ULL, 0x5cb0a9dcbd41fbd4ULL, 0x76f988da831153b5ULL, 0x983e5152ee66dfabULL,
+    0xa831c66d2db43210ULL, 0xb00327c898fb213fULL, 0xbf597fc7beef0ee4ULL, 0xc6e00bf33da88fc2ULL, 0xd5a79147930aa725ULL,
+    0x06ca6351e003826fULL, 0x142929670a0e6e70ULL, 0x27b70a8546d22ffcULL, 0x2e1b21385c26c926ULL, 0x4d2c6dfc5ac42aedULL,
+    0x53380d139d95b3dfULL, 0x650a73548baf63deULL, 0x766a0abb3c77b2a8ULL, 0x81c2c92e47edaee6ULL, 0x92722c851482353bULL,
+    0xa2bfe8a14cf10364ULL, 0xa81a664bbc423001ULL, 0xc24b8b70d0f89791ULL, 0xc76c51a30654be30ULL, 0xd192e819d6ef5218ULL,
+    0xd69906245565a910ULL, 0xf40e35855771202aULL, 0x106aa07032bbd1b8ULL, 0x19a4c116b8d2d0c8ULL, 0x1e376c085141ab53ULL,
+    0x2748774cdf8eeb99ULL, 0x34b0bcb5e19b48a8ULL, 0x391c0cb3c5c95a63ULL, 0x4ed8aa4ae3418acbULL, 0x5b9cca4f7763e373ULL,
+    0x682e6ff3d6b2b8a3ULL, 0x748f82ee5defb2fcULL, 0x78a5636f43172f60ULL, 0x84c87814a1f0ab72ULL, 0x8cc702081a6439ecULL,
+    0x90befffa23631e28ULL, 0xa4506cebde82bde9ULL, 0xbef9a3f7b2c67915ULL, 0xc67178f2e372532bULL, 0xca273eceea26619cULL,
+    0xd186b8c721c0c207ULL, 0xeada7dd6cde0eb1eULL, 0xf57d4f7fee6ed178ULL, 0x06f067aa72176fbaULL, 0x0a637dc5a2c898a6ULL,
+    0x113f9804bef90daeULL, 0x1b710b35131c471bULL, 0x28db77f523047d84ULL, 0x32caab7b40c72493ULL, 0x3c9ebe0a15c9bebcULL,
+    0x431d67c49c100d4cULL, 0x4cc5d4becb3e42b6ULL, 0x597f299cfc657e2aULL, 0x5fcb6fab3ad6faecULL, 0x6c44198c4a475817ULL};
+
+#define ROR64(x, n) (((x) >> (n)) | ((x) << (64 - (n))))
+
+/* single-block SHA-512 of a 16-byte message (idx || iter) */
+static void sha512_16(const uint8_t msg[16], uint8_t digest[64])
+{
+    uint64_t h[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                     0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    uint8_t blk[128];
+    memset(blk, 0, 128);
+    memcpy(blk, msg, 16);
+    blk[16] = 0x80;
+    blk[127] = 128; /* message length in bits, big-endian */
+    uint64_t w[80];
+    for (int i = 0; i < 16; i++) {
+        uint64_t v = 0;
+        for (int j = 0; j < 8; j++) v = (v << 8) | blk[8 * i + j];
+        w[i] = v;
+    }
+    for (int i = 16; i < 80; i++) {
+        uint64_t s0 = ROR64(w[i - 15], 1) ^ ROR64(w[i - 15], 8) ^ (w[i - 15] >> 7);
+        uint64_t s1 = ROR64(w[i - 2], 19) ^ ROR64(w[i - 2], 61) ^ (w[i - 2] >> 6);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 80; i++) {
+        uint64_t S1 = ROR64(e, 14) ^ ROR64(e, 18) ^ ROR64(e, 41);
+        uint64_t ch = (e & f) ^ (~e & g);
+        uint64_t t1 = hh + S1 + ch + K512[i] + w[i];
+        uint64_t S0 = ROR64(a, 28) ^ ROR64(a, 34) ^ ROR64(a, 39);
+        uint64_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint64_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) digest[8 * i + j] = (uint8_t)(h[i] >> (56 - 8 * j));
+}
+
+/* SHA512_rng<Fr>(idx): hash (idx, iter) little-endian, take the low 256 bits as
+ * limbs, clear bits above the modulus MSB (bits 254, 255), reject if >= r,
+ * then convert to Montgomery form.  rng.tcc:26-72 */
+static void sha512_rng_fr(fp_t *o, uint64_t idx)
+{
+    uint64_t iter = 0;
+    uint64_t rv[4];
+    do {
+        uint8_t msg[16], dg[64];
+        memcpy(msg, &idx, 8);
+        memcpy(msg + 8, &iter, 8);
+        sha512_16(msg, dg);
+        memcpy(rv, dg, 32);
+        rv[3] &= 0x3fffffffffffffffULL;
+        ++iter;
+    } while (limbs_geq(rv, FR.m));
+    fp_from_bigint(o, rv, &FR);
+}
+
+/* ------------------------------------------------------------------ */
+/* exported entry points                                                */
+/* ------------------------------------------------------------------ */
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+int orc_msm_g1(const uint64_t *bases, const uint64_t *scalars, size_t n, size_t chunks, int variant, int normalise, uint64_t *out)
+{
+    return g1_msm_entry(bases, scalars, n, chunks, variant, normalise, out);
+}
+int orc_msm_g2(const uint64_t *bases, const uint64_t *scalars, size_t n, size_t chunks, int variant, int normalise, uint64_t *out)
+{
+    return g2_msm_entry(bases, scalars, n, chunks, variant, normalise, out);
+}
+int orc_batch_exp_g1(const uint64_t *base, const uint64_t *scalars, size_t n, const uint64_t *coeff, size_t window, int normalise, uint64_t *out)
+{
+    return g1_batch_exp_entry(base, scalars, n, coeff, window, normalise, out, G1_WTAB, 22);
+}
+int orc_batch_exp_g2(const uint64_t *base, const uint64_t *scalars, size_t n, const uint64_t *coeff, size_t window, int normalise, uint64_t *out)
+{
+    return g2_batch_exp_entry(base, scalars, n, coeff, window, normalise, out, G2_WTAB, 22);
+}
+size_t orc_exp_window_size_g1(size_t n) { return orc_exp_window_size(G1_WTAB, 22, n); }
+size_t orc_exp_window_size_g2(size_t n) { return orc_exp_window_size(G2_WTAB, 22, n); }
+
+int orc_batch_to_special_g1(uint64_t *pts, size_t n) { g1_batch_to_special((g1_t *)pts, n); return 0; }
+int orc_batch_to_special_g2(uint64_t *pts, size_t n) { g2_batch_to_special((g2_t *)pts, n); return 0; }
+
+int orc_g1_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) { return g1_op_entry(op, a, b, n, out); }
+int orc_g2_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) { return g2_op_entry(op, a, b, n, out); }
+
+int orc_scalar_mul_g1(const uint64_t *base, const uint64_t *scalars, size_t n, int stride_base, int normalise, uint64_t *out)
+{
+    return g1_scalar_mul_entry(base, scalars, n, stride_base, normalise, out);
+}
+int orc_scalar_mul_g2(const uint64_t *base, const uint64_t *scalars, size_t n, int stride_base, int normalise, uint64_t *out)
+{
+    return g2_scalar_mul_entry(base, scalars, n, stride_base, normalise, out);
+}
+
+static int fp_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out, const fpctx_t *c)
+{
+    for (size_t i = 0; i < n; i++) {
+        fp_t x, y, r;
+        memcpy(x.l, a + 4 * i, 32);
+        if (b) memcpy(y.l, b + 4 * i, 32); else memset(y.l, 0, 32);
+        switch (op) {
+        case 0: fp_mul(&r, &x, &y, c); break;
+        case 1: fp_mul(&r, &x, &x, c); break;
+        case 2: fp_add(&r, &x, &y, c); break;
+        case 3: fp_sub(&r, &x, &y, c); break;
+        case 4: fp_inv(&r, &x, c); break;
+        case 5: fp_neg(&r, &x, c); break;
+        default: return 1;
+        }
+        memcpy(out + 4 * i, r.l, 32);
+    }
+    return 0;
+}
+int orc_fq_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) { return fp_op(op, a, b, n, out, &FQ); }
+int orc_fr_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) { return fp_op(op, a, b, n, out, &FR); }
+
+int orc_fq2_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out)
+{
+    for (size_t i = 0; i < n; i++) {
+        fq2_t x, y, r;
+        memcpy(&x, a + 8 * i, 64);
+        if (b) memcpy(&y, b + 8 * i, 64); else memset(&y, 0, 64);
+        switch (op) {
+        case 0: fq2_mul(&r, &x, &y); break;
+        case 1: fq2_sqr(&r, &x); break;
+        case 2: fq2_add(&r, &x, &y); break;
+        case 3: fq2_sub(&r, &x, &y); break;
+        case 4: fq2_inv(&r, &x); break;
+        case 5: fq2_neg(&r, &x); break;
+        default: return 1;
+        }
+        memcpy(out + 8 * i, &r, 64);
+    }
+    return 0;
+}
+
+int orc_fr_from_bigint(const uint64_t *a, size_t n, uint64_t *out)
+{
+    for (size_t i = 0; i < n; i++) {
+        fp_t r;
+        fp_from_bigint(&r, a + 4 * i, &FR);
+        memcpy(out + 4 * i, r.l, 32);
+    }
+    return 0;
+}
+int orc_fr_as_bigint(const uint64_t *a, size_t n, uint64_t *out)
+{
+    for (size_t i = 0; i < n; i++) fp_as_bigint(out + 4 * i, a + 4 * i, &FR);
+    return 0;
+}
+int orc_fq_from_bigint(const uint64_t *a, size_t n, uint64_t *out)
+{
+    for (size_t i = 0; i < n; i++) {
+        fp_t r;
+        fp_from_bigint(&r, a + 4 * i, &FQ);
+        memcpy(out + 4 * i, r.l, 32);
+    }
+    return 0;
+}
+
+int orc_sha512_rng_fr(uint64_t idx0, size_t n, uint64_t *out)
+{
+#pragma omp parallel for
+    for (size_t i = 0; i < n; i++) {
+        fp_t r;
+        sha512_rng_fr(&r, idx0 + i);
+        memcpy(out + 4 * i, r.l, 32);
+    }
+    return 0;
+}
+
+/* G1_one = (1,2,1): alt_bn128_init.cpp:148-150 ; G2_one: :209-213 */
+int orc_g1_one(uint64_t *out)
+{
+    g1_t g;
+    const uint64_t one[4] = {1, 0, 0, 0}, two[4] = {2, 0, 0, 0};
+    fp_from_bigint(&g.X, one, &FQ);
+    fp_from_bigint(&g.Y, two, &FQ);
+    fq_set_one(&g.Z);
+    memcpy(out, &g, sizeof g);
+    return 0;
+}
+
+int orc_g2_one(uint64_t *out)
+{
+    /* decimal constants of alt_bn128_init.cpp:209-212 as little-endian limbs */
+    static const uint64_t XC0[4] = {0x46debd5cd992f6edULL, 0x674322d4f75edaddULL, 0x426a00665e5c4479ULL, 0x1800deef121f1e76ULL};
+    static const uint64_t XC1[4] = {0x97e485b7aef312c2ULL, 0xf1aa493335a9e712ULL, 0x7260bfb731fb5d25ULL, 0x198e9393920d483aULL};
+    static const uint64_t YC0[4] = {0x4ce6cc0166fa7daaULL, 0xe3d1e7690c43d37bULL, 0x4aab71808dcb408fULL, 0x12c85ea5db8c6debULL};
+    static const uint64_t YC1[4] = {0x55acdadcd122975bULL, 0xbc4b313370b38ef3ULL, 0xec9e99ad690c3395ULL, 0x090689d0585ff075ULL};
+    g2_t g;
+    fp_from_bigint(&g.X.c0, XC0, &FQ);
+    fp_from_bigint(&g.X.c1, XC1, &FQ);
+    fp_from_bigint(&g.Y.c0, YC0, &FQ);
+    fp_from_bigint(&g.Y.c1, YC1, &FQ);
+    fq2_set_one(&g.Z);
+    memcpy(out, &g, sizeof g);
+    return 0;
+}
