@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py — G1 MSM points/s on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 20] [--group g1]
+    python bench.py --impl reference ...      # the reference's CPU multi_exp on the host cores
+
+A "step" is one multi-scalar multiplication of n = 2^log2n synthetic points per GPU
+(config 2 of BASELINE.json at the default 2^20): uniform random scalars, bases k_i*G made on
+the device by the fixed-base kernel.  Numbers on the JSON line:
+
+  value   whole-job points/s with bases resident in HBM (CommitmentKey) and scalars already
+          on the device; timed with CUDA events on the launching stream around the C-ABI
+          call, which includes the D2H of the W window sums and the host Horner tail.
+  e2e     the same MSM through the reference-facing host call b200_msm_g1 (== libff::multi_exp
+          signature: host Jacobian bases + host scalars, here in pinned memory): H2D of
+          bases and scalars, Jacobian->affine ingest, MSM, D2H, host tail, all inside the
+          timed region.
+  roofline  k_accumulate (the bucket mixed-addition kernel, >80 % of the step) against the
+          MEASURED IMAD.WIDE.U32 peak of this GPU (b200_imad_peak), canonical count of
+          SURVEY.md §8(d): 11 modmul per mixed add x 136 multiply-adds per modmul; plus
+          the gather traffic against the measured HBM copy bandwidth.
+  cpu_baseline  libff's multi_exp<BDLO12> (oracle/_ref, built from the unmodified reference)
+          on this box's host cores over a bounded sample of the same workload.
+
+With N > 1 (torchrun) every rank owns the index range of an N * 2^log2n-point MSM
+(weak scaling): it runs the whole pipeline on its slice, the 96-byte partials are
+all-gathered and summed on the host (no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+MONT_R = 1 << 256
+METRIC = "g1_msm_points_per_s"
+UNIT = "points/s"
+
+
+def limbs(x, n=4):
+    return np.array([(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)], dtype=np.uint64)
+
+
+def generator(group):
+    """G1_one = (1, 2, 1) / G2_one (alt_bn128_init.cpp:148-150, 209-213), Montgomery limbs."""
+    m = lambda v: limbs(v * MONT_R % Q)
+    if group == "g1":
+        return np.concatenate([m(1), m(2), m(1)])
+    xc0 = 10857046999023057135944570762232829481370756359578518086990519993285655852781
+    xc1 = 11559732032986387107991004021392285783925812861821192530917403151452391805634
+    yc0 = 8495653923123431417604973247489272438418190587263600148770280649306958101930
+    yc1 = 4082367875863433681332203403145435568316851327593401208105741076214120093531
+    return np.concatenate([m(xc0), m(xc1), m(yc0), m(yc1), m(1), m(0)])
+
+
+def random_scalars(n, seed):
+    """Uniform 253-bit integers read as Montgomery images (every residue < r is one)."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)
+    return a
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def checker():
+    from oracle.binding import Checker
+    if Checker.available("ref"):
+        try:
+            return Checker("ref"), "reference"
+        except Exception:
+            pass
+    return Checker("orc"), "port"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: libff multi_exp<BDLO12> with chunks = host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    chk, kind = checker()
+    group = args.group
+    m = 1 << min(args.log2n, args.ref_log2n)
+    k = chk.sha512_rng_fr(1 << 40, m)
+    P = chk.batch_exp(group, chk.one(group), k, normalise=True)
+    s = chk.sha512_rng_fr(0, m)
+    threads = chk.max_threads()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        chk.msm(group, P, s, chunks=threads, variant=0)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = m / (ms * 1e-3)
+    sample = f"{group} multi_exp<BDLO12> of 2^{int(np.log2(m))} points per step, chunks={threads}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC.replace("g1", group), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 limbs (254-bit modular integer)", "data": "synthetic",
+        "config": {"workload": f"{group} MSM 2^{args.log2n} points per GPU (BASELINE.json configs[1])",
+                   "reference_sample_points": m},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=20, help="points per GPU = 2^log2n")
+    ap.add_argument("--group", default="g1", choices=["g1", "g2"])
+    ap.add_argument("--ref-log2n", type=int, default=17, help="sample size of the CPU reference legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import legosnark_b200 as lb
+    from legosnark_b200 import multi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lb.init_devices([local_rank])
+
+    group = args.group
+    n = 1 << args.log2n
+    L = 12 if group == "g1" else 24
+    A = 8 if group == "g1" else 16
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- synthetic inputs: scalars on host (pinned) and device, bases k_i * G made on the device ----
+    s_host = torch.from_numpy(random_scalars(n, 1000 + rank).view(np.int64)).pin_memory()
+    k_host = torch.from_numpy(random_scalars(n, 2000 + rank).view(np.int64))
+    d_s = s_host.to(dev)
+    d_k = k_host.to(dev)
+    table = lb.get_window_table(group, 254, 0, generator(group), expected_scalars=n)
+    d_aff = torch.empty((n, A), dtype=torch.int64, device=dev)
+    lb.batch_exp_device(table, d_k.data_ptr(), n, d_aff.data_ptr(), stream)
+    torch.cuda.synchronize()
+    table.close()
+    key = lb.CommitmentKey(group, device_affine_ptr=d_aff.data_ptr(), n=n)
+    # host image of the same bases in the reference layout (Jacobian, Z = 1), pinned
+    jac_host = torch.empty((n, L), dtype=torch.int64).pin_memory()
+    jac_host[:, :A] = d_aff.cpu()
+    one_z = torch.from_numpy(generator(group)[A:].view(np.int64).copy())
+    jac_host[:, A:] = one_z
+    del d_k, d_aff
+    s_np = s_host.numpy().view(np.uint64)
+    jac_np = jac_host.numpy().view(np.uint64)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step_resident():
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        ev0.record()
+        part = key.multi_exp_device(d_s.data_ptr(), n, 0, stream)
+        ev1.record()
+        ev1.synchronize()
+        dev_ms = ev0.elapsed_time(ev1)
+        t0 = time.perf_counter()
+        res = multi.sharded_multi_exp(group, part, dev) if world > 1 else part
+        gather_ms = (time.perf_counter() - t0) * 1e3 if world > 1 else 0.0
+        return res, dev_ms + gather_ms, lb.last_stats()
+
+    def step_e2e():
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        part = lb.multi_exp(group, jac_np, s_np)
+        res = multi.sharded_multi_exp(group, part, dev) if world > 1 else part
+        return res, (time.perf_counter() - t0) * 1e3, lb.last_stats()
+
+    # ---- measured denominators -------------------------------------------------------
+    imad_wide_peak, _ = lb.imad_peak(0, 1 << 14)
+    imad32_peak, _ = lb.imad_peak(1, 1 << 14)
+    modmul_peak, _ = lb.imad_peak(2, 1 << 9)
+    hbm_gbs, hbm_src = measured_peaks()
+
+    # ---- warm-up, then exactly K timed steps of each flavour ----------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    time.sleep(0.25)
+    t_start = time.perf_counter()
+    res_ms, acc_ms, fin_us = [], [], []
+    result = None
+    for _ in range(args.steps):
+        result, ms, st = step_resident()
+        res_ms.append(ms)
+        acc_ms.append(st["accumulate_ms"])
+        fin_us.append(st["host_finalize_us"])
+    barrier()
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_start, t_end)
+    stats = st
+
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        res2, ms, st2 = step_e2e()
+        e2e_ms.append(ms)
+    barrier()
+    assert (res2 == result).all(), "host-buffer path and resident path disagree"
+
+    tot_res, tot_e2e = float(np.sum(res_ms)), float(np.sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([tot_res, tot_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_res, tot_e2e = float(t[0]), float(t[1])
+    ms_per_step = tot_res / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    e2e_value = world * n / (tot_e2e / args.steps * 1e-3)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------
+    acc = float(np.mean(acc_ms))
+    entries = stats["num_entries"]
+    MODMUL_MIXED = {"g1": 11, "g2": 29}[group]      # canonical madd-2007-bl count, SURVEY.md §8(d)
+    MODMUL_ACTUAL = {"g1": 10, "g2": 28}[group]     # XYZZ madd-2008-s: 8M+2S (Fq2: 8*3 + 2*2)
+    imads = entries * MODMUL_MIXED * 136.0
+    achieved = imads / (acc * 1e-3) / 1e12
+    gather_bytes = entries * ({"g1": 64, "g2": 128}[group] + 4.0)
+    roofline = {
+        "bound": "imad", "kernel": f"k_accumulate<{'Fq' if group == 'g1' else 'Fq2'}>",
+        "achieved": achieved, "peak": imad_wide_peak / 1e12, "unit": "T multiply-add/s (32x32+64, lane-ops)",
+        "frac": achieved / (imad_wide_peak / 1e12), "traffic": None,
+        "peak_source": "measured live: b200_imad_peak(IMAD.WIDE.U32), all SMs",
+        "ms_per_launch": acc, "share_of_step": acc / (float(np.mean(res_ms))),
+        "algorithmic": {"mixed_adds_per_launch": entries, "modmul_per_mixed_add": MODMUL_MIXED,
+                        "imad_per_modmul": 136, "modmul_per_mixed_add_executed": MODMUL_ACTUAL},
+        "modmul_per_s": entries * MODMUL_ACTUAL / (acc * 1e-3), "modmul_per_s_peak_measured": modmul_peak,
+        "imad32_peak": imad32_peak / 1e12,
+        "hbm": {"gather_bytes_per_launch": gather_bytes, "achieved_gbs": gather_bytes / (acc * 1e-3) / 1e9,
+                "peak_gbs": hbm_gbs, "peak_source": hbm_src, "frac": gather_bytes / (acc * 1e-3) / 1e9 / hbm_gbs},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1), with a parity check on the sample ----------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        chk, kind = checker()
+        m = 1 << min(args.log2n, args.ref_log2n + 1)
+        threads = chk.max_threads()
+        t0 = time.perf_counter()
+        want = chk.msm(group, jac_np[:m], s_np[:m], chunks=threads, variant=0)
+        dt = time.perf_counter() - t0
+        got = key.multi_exp(s_np[:m])
+        assert (got == want).all(), "GPU result differs from the CPU reference on the baseline sample"
+        cpu = {"value": m / dt, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"first 2^{int(np.log2(m))} points of the workload, multi_exp<BDLO12> chunks={threads}, {dt:.2f} s; "
+                         "GPU result on the same sample bit-identical"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC.replace("g1", group), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (254-bit modular integer, 8x32-bit Montgomery)", "data": "synthetic",
+            "config": {"workload": f"{group} MSM 2^{args.log2n} points per GPU (BASELINE.json configs[1])",
+                       "points_per_gpu": n, "window_bits": stats["window_bits"], "windows": stats["num_windows"],
+                       "scalars": "uniform 253-bit", "bases": "k_i*G, distinct, resident in HBM for `value`",
+                       "l2": "flushed between timed iterations (512 MiB write)", "sharding": f"index range x{world}, host sum of partials"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": stats2_bytes(st2, "h2d_bytes") * world,
+                    "d2h_bytes_per_step": stats2_bytes(st2, "d2h_bytes") * world, "ms_per_step": tot_e2e / args.steps,
+                    "path": "b200_msm_* with pinned host Jacobian bases + scalars (cold key)"},
+            "gpu_launches": int(stats["kernel_launches"]) * args.steps,
+            "launches_per_step": int(stats["kernel_launches"]),
+            "host_finalize_us": float(np.mean(fin_us)),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }), flush=True)
+    key.close()
+    lb.shutdown()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stats2_bytes(st, k):
+    return float(st[k])
+
+
+if __name__ == "__main__":
+    main()

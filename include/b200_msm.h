@@ -1,0 +1,170 @@
+/* b200_msm.h — C-ABI of the B200-native MSM / fixed-base batch_exp engine that
+ * drops in behind libff's scalar_multiplication templates as used by LegoSNARK.
+ *
+ * The reference has no FFI: its boundary is a set of C++ function templates in
+ *   LFF/algebra/scalar_multiplication/multiexp.hpp
+ * (LFF = depends/libsnark/depends/libff/libff) instantiated in the caller's TU.
+ * legosnark_b200/shim/libff/algebra/scalar_multiplication/multiexp.hpp shadows
+ * that header and forwards the four concrete groups (alt_bn128 / bn128 G1, G2)
+ * to the entry points below; INTEGRATION.md shows the binding.
+ *
+ * Data layout (identical to the reference's in-memory objects, so callers pass
+ * &vec[0] reinterpret-cast, no repacking):
+ *   Fr / Fq element : 4 x u64 little-endian limbs, Montgomery form, R = 2^256
+ *                     (fp.hpp:42 mont_repr; bn::Fp, ATE/include/zm2.h:266)
+ *   G1 point        : X | Y | Z             = 12 limbs = 96 B, Jacobian, Z == 0 <=> zero
+ *                     (alt_bn128_g1.hpp:35; bn128_g1.hpp:36 coord[3])
+ *   G2 point        : X.c0 X.c1 | Y.c0 Y.c1 | Z.c0 Z.c1 = 24 limbs = 192 B
+ *                     (alt_bn128_g2.hpp:36; bn128_g2.hpp coord[3] of Fp2T{a_,b_})
+ * Bases may be zero, repeated, and non-normalised Jacobian (Z != 1).
+ * Point outputs are normalised: (x, y, 1) in Montgomery form, or the zero
+ * (0, 1, 0) of alt_bn128 (the shim rewrites it to bn128's (1,1,0)).  Results
+ * equal the reference's as group elements and bit-for-bit after
+ * to_affine_coordinates().
+ *
+ * Every function returns 0 on success; otherwise b200_last_error() describes the
+ * failure.  There is NO CPU fallback: without a CUDA device b200_init fails and
+ * every compute entry point returns an error.  Calls are serialised per process
+ * by an internal mutex (every shipped caller is single-threaded).
+ */
+#ifndef B200_MSM_H
+#define B200_MSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_CUDA 1
+#define B200_ERR_ARG 2
+#define B200_ERR_NOT_INIT 3
+#define B200_ERR_NO_DEVICE 4
+
+/* ---- lifecycle ------------------------------------------------------------- */
+/* Use devices 0..n_gpus-1 (n_gpus <= 0: all visible).  An MSM / batch_exp call is
+ * sharded by index range across them (multiexp.tcc:417-438 does the same across
+ * OpenMP threads) and the per-GPU partials are summed on the host. */
+int b200_init(int n_gpus);
+/* Use exactly these CUDA device ordinals (one process per GPU under torchrun: {LOCAL_RANK}). */
+int b200_init_devices(const int *device_ids, int n);
+void b200_shutdown(void);
+int b200_device_count(void); /* devices in use; 0 before init */
+const char *b200_last_error(void);
+const char *b200_version(void);
+
+/* ---- multi_exp / multi_exp_with_mixed_addition  (multiexp.hpp:56-61, 70-75;
+ *      multiexp.tcc:402-441, 443-496, inner BDLO12 :165-282) ---------------------
+ * out = sum_i scalars[i] * bases[i].  `Method` and `chunks` of the reference are
+ * hints that do not change the group element; every variant maps here. */
+int b200_msm_g1(const uint64_t *bases /* n x 12 */, const uint64_t *scalars_mont /* n x 4 */, size_t n,
+                uint64_t out[12]);
+int b200_msm_g2(const uint64_t *bases /* n x 24 */, const uint64_t *scalars_mont /* n x 4 */, size_t n,
+                uint64_t out[24]);
+
+/* Host-side sum of partial results (north star: "each GPU returns a partial group element,
+ * and the partials are summed on the host"; the serial sum at multiexp.tcc:433-438).  Used by
+ * the engine for its own per-device partials and by one-process-per-GPU launchers (bench.py
+ * under torchrun) for the per-rank partials.  Pure host code: needs no device. */
+int b200_sum_partials_g1(const uint64_t *pts /* n x 12, any Jacobian */, size_t n, uint64_t out[12]);
+int b200_sum_partials_g2(const uint64_t *pts /* n x 24 */, size_t n, uint64_t out[24]);
+
+/* ---- resident commitment keys ------------------------------------------------
+ * LegoSNARK commits many vectors under one key (CommScheme::commit,
+ * LS/prototools/commit.h:149-158; CPPoly::prove uses prefixes of the same g1s,
+ * LS/gadgets/poly.h:77-88).  pin uploads + normalises the bases once (sharded
+ * over the devices in use); msm_pinned then only moves scalars.  offset/n select
+ * the sub-range [offset, offset+n) of the key. */
+int b200_pin_bases_g1(const uint64_t *bases, size_t n, uint64_t *handle);
+int b200_pin_bases_g2(const uint64_t *bases, size_t n, uint64_t *handle);
+int b200_unpin_bases(uint64_t handle);
+int b200_msm_pinned_g1(uint64_t handle, size_t offset, const uint64_t *scalars_mont, size_t n, uint64_t out[12]);
+int b200_msm_pinned_g2(uint64_t handle, size_t offset, const uint64_t *scalars_mont, size_t n, uint64_t out[24]);
+
+/* Scalars already in device memory (cudaMalloc / torch) on the handle's first
+ * device; all kernels are enqueued on `cuda_stream` (a cudaStream_t, NULL = the
+ * engine's own stream) so the caller can bracket the call with its own events.
+ * Single-device only.  Used by bench.py for the HBM-resident `value` number. */
+int b200_msm_pinned_dev_g1(uint64_t handle, size_t offset, const void *d_scalars_mont, size_t n, void *cuda_stream,
+                           uint64_t out[12]);
+int b200_msm_pinned_dev_g2(uint64_t handle, size_t offset, const void *d_scalars_mont, size_t n, void *cuda_stream,
+                           uint64_t out[24]);
+
+/* ---- fixed-base: get_window_table + batch_exp / batch_exp_with_coeff
+ *      (multiexp.hpp:96-124; multiexp.tcc:509-681) --------------------------------
+ * out[i] = (coeff * scalars[i]) * base   (coeff_mont == NULL: no coefficient).
+ * The reference's window_table layout is not observable by any caller
+ * (SURVEY.md §8b); the engine builds its own affine table on the device with a
+ * window chosen for the GPU.  Outputs are normalised (batch_to_special form). */
+size_t b200_exp_window_size_g1(size_t num_scalars); /* libff's table: alt_bn128_init.cpp:157-201 */
+size_t b200_exp_window_size_g2(size_t num_scalars); /* alt_bn128_init.cpp:220-264 */
+int b200_batch_exp_g1(const uint64_t base[12], const uint64_t *scalars_mont, size_t n, const uint64_t *coeff_mont,
+                      uint64_t *out /* n x 12 */);
+int b200_batch_exp_g2(const uint64_t base[24], const uint64_t *scalars_mont, size_t n, const uint64_t *coeff_mont,
+                      uint64_t *out /* n x 24 */);
+/* table reuse across calls (r1cs_gg_ppzksnark.tcc:296-360 builds one G1 and one G2 table
+ * and runs five batch_exps over them) */
+int b200_window_table_create_g1(const uint64_t base[12], size_t expected_scalars, uint64_t *handle);
+int b200_window_table_create_g2(const uint64_t base[24], size_t expected_scalars, uint64_t *handle);
+int b200_window_table_destroy(uint64_t handle);
+int b200_batch_exp_table_g1(uint64_t handle, const uint64_t *scalars_mont, size_t n, const uint64_t *coeff_mont,
+                            uint64_t *out);
+int b200_batch_exp_table_g2(uint64_t handle, const uint64_t *scalars_mont, size_t n, const uint64_t *coeff_mont,
+                            uint64_t *out);
+/* device-resident variant: scalars in, affine points (x|y, 8 resp. 16 limbs each, (0,0) = zero)
+ * out, both in device memory; enqueued on cuda_stream.  Doubles as the on-device generator of
+ * benchmark bases k_i * G. */
+int b200_batch_exp_table_dev_g1(uint64_t handle, const void *d_scalars_mont, size_t n, void *d_out_affine,
+                                void *cuda_stream);
+int b200_batch_exp_table_dev_g2(uint64_t handle, const void *d_scalars_mont, size_t n, void *d_out_affine,
+                                void *cuda_stream);
+/* pin bases that already sit in device memory in the affine layout above (no copy is taken of
+ * host data; the engine copies device-to-device) */
+int b200_pin_affine_dev_g1(const void *d_affine, size_t n, uint64_t *handle);
+int b200_pin_affine_dev_g2(const void *d_affine, size_t n, uint64_t *handle);
+
+/* ---- batch_to_special (multiexp.hpp:126-127; multiexp.tcc:683-715;
+ *      alt_bn128_g1.cpp:499-521; field_utils.tcc:171-194) ----------------------------
+ * In place: every non-zero point becomes (X/Z^2, Y/Z^3, 1); zeros become (0,1,0). */
+int b200_batch_to_affine_g1(uint64_t *pts, size_t n);
+int b200_batch_to_affine_g2(uint64_t *pts, size_t n);
+
+/* ---- parity hooks: element-wise kernels over the device arithmetic ------------
+ * field: 0 Fq, 1 Fr, 2 Fq2.  op: 0 mul, 1 sqr, 2 add, 3 sub, 4 inverse, 5 neg,
+ * 6 as_bigint (Fq/Fr), 7 from bigint (Fq/Fr).  b may be NULL for unary ops. */
+int b200_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
+/* group: 0 G1, 1 G2; Jacobian in / Jacobian out (not normalised).
+ * op: 0 a+b, 1 a + affine b (mixed), 2 2a, 6 a - affine b, 7 k*a, 8 Jacobian->XYZZ->Jacobian */
+int b200_test_group_op(int group, int op, const uint64_t *a, const uint64_t *b, size_t n, uint32_t k,
+                       uint64_t *out);
+
+/* ---- introspection for bench.py / profiling ------------------------------------ */
+typedef struct {
+    uint64_t n;                /* points in the last MSM (per device 0) */
+    uint32_t window_bits;      /* c */
+    uint32_t num_windows;      /* W */
+    uint32_t chunk_len;        /* max entries per accumulation task */
+    uint32_t kernel_launches;  /* kernels launched by the last call on device 0 */
+    uint64_t num_tasks;        /* accumulation tasks */
+    double host_finalize_us;   /* Horner + normalise on the host */
+    double h2d_bytes;          /* bytes copied host->device by the last call */
+    double d2h_bytes;
+    uint64_t num_entries;      /* bucket entries = mixed additions done by k_accumulate (device 0) */
+    double accumulate_ms;      /* CUDA-event time of k_accumulate on device 0 */
+    double device_ms;          /* CUDA-event time of the whole enqueued pipeline on device 0 */
+} b200_stats_t;
+int b200_last_stats(b200_stats_t *out);
+/* Overrides for tuning / tests: window bits c (0 = auto), chunk length L (0 = auto). */
+int b200_set_tuning(int window_bits, int chunk_len);
+/* IMAD roofline microbenchmark: runs `iters` rounds of independent
+ * IMAD.WIDE.U32 chains on every SM of device 0 and returns multiply-adds
+ * (lane-ops) per second.  kind: 0 IMAD.WIDE.U32 (32x32+64), 1 IMAD (32x32+32 lo),
+ * 2 Montgomery multiplications per second (Fq::mul chains). */
+int b200_imad_peak(int kind, int iters, double *ops_per_sec, double *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_MSM_H */

@@ -1,0 +1,309 @@
+"""legosnark_b200 — B200-native MSM / fixed-base batch_exp engine behind libff's
+scalar_multiplication API, as used by LegoSNARK.
+
+This module is the Python host-side mirror of the reference interface
+(LFF/algebra/scalar_multiplication/multiexp.hpp, LFF = depends/libsnark/depends/
+libff/libff): same function names, argument meaning and zero/edge behaviour,
+over numpy ``uint64`` arrays holding the reference's in-memory objects
+(Montgomery limbs, R = 2^256):
+
+    Fr scalars  (n, 4)      G1 points (n, 12) = X|Y|Z      G2 points (n, 24)
+
+All arithmetic happens in ``libb200msm.so`` (CUDA, sm_100a) through the C-ABI in
+``include/b200_msm.h``; the C++ drop-in header lives in ``legosnark_b200/shim``.
+There is no CPU fallback: importing works anywhere, but every compute call
+raises ``B200Error`` without the built library and a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+__all__ = [
+    "B200Error", "init", "init_devices", "shutdown", "device_count", "lib", "library_path",
+    "multi_exp", "multi_exp_with_mixed_addition", "get_exp_window_size", "get_window_table", "batch_exp",
+    "batch_exp_with_coeff", "batch_to_special", "CommitmentKey", "sum_partials", "shard_range", "WindowTable", "last_stats", "set_tuning",
+    "imad_peak", "test_field_op", "test_group_op",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb200msm.so")
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_LIMBS = {"g1": 12, "g2": 24}
+_AFFINE_LIMBS = {"g1": 8, "g2": 16}
+
+# multi_exp_method (multiexp.hpp:20-47): every method computes the same group element; the engine
+# runs its own Pippenger for all of them.
+multi_exp_method_naive = 0
+multi_exp_method_naive_plain = 1
+multi_exp_method_bos_coster = 2
+multi_exp_method_BDLO12 = 3
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_uint64), ("window_bits", ctypes.c_uint32), ("num_windows", ctypes.c_uint32),
+                ("chunk_len", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32), ("num_tasks", ctypes.c_uint64),
+                ("host_finalize_us", ctypes.c_double), ("h2d_bytes", ctypes.c_double), ("d2h_bytes", ctypes.c_double),
+                ("num_entries", ctypes.c_uint64), ("accumulate_ms", ctypes.c_double), ("device_ms", ctypes.c_double)]
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load the C-ABI library; fails loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise B200Error(
+                f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). legosnark_b200 has no CPU fallback.")
+        L = ctypes.CDLL(_LIB_PATH)
+        L.b200_last_error.restype = ctypes.c_char_p
+        L.b200_version.restype = ctypes.c_char_p
+        L.b200_exp_window_size_g1.restype = ctypes.c_size_t
+        L.b200_exp_window_size_g1.argtypes = [ctypes.c_size_t]
+        L.b200_exp_window_size_g2.restype = ctypes.c_size_t
+        L.b200_exp_window_size_g2.argtypes = [ctypes.c_size_t]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise B200Error(f"{what} failed (code {rc}): {lib().b200_last_error().decode()}")
+
+
+def _arr(a, width):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, width)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_u64p)
+
+
+def _sz(n):
+    return ctypes.c_size_t(int(n))
+
+
+def _vp(x):
+    return ctypes.c_void_p(int(x)) if x else ctypes.c_void_p(0)
+
+
+# ---- lifecycle -------------------------------------------------------------------
+def init(n_gpus: int = 1):
+    _check(lib().b200_init(int(n_gpus)), "b200_init")
+
+
+def init_devices(ids):
+    arr = (ctypes.c_int * len(ids))(*ids)
+    _check(lib().b200_init_devices(arr, len(ids)), "b200_init_devices")
+
+
+def shutdown():
+    if _lib is not None:
+        _lib.b200_shutdown()
+
+
+def device_count() -> int:
+    return int(lib().b200_device_count())
+
+
+# ---- multi_exp / multi_exp_with_mixed_addition (multiexp.hpp:56-75) ----------------
+def multi_exp(group, bases, scalars, chunks: int = 1, method: int = multi_exp_method_BDLO12):
+    """sum_i scalars[i] * bases[i]; returns the normalised point (12 or 24 limbs).
+
+    ``chunks`` and ``method`` are accepted for signature parity (multiexp.tcc:402-441);
+    they never change the group element.  ``len(bases) == 0`` returns zero like the reference."""
+    L = _LIMBS[group]
+    bases, scalars = _arr(bases, L), _arr(scalars, 4)
+    if bases.shape[0] != scalars.shape[0]:
+        raise ValueError("bases and scalars differ in length")  # assert at multiexp.tcc:450
+    out = np.zeros(L, dtype=np.uint64)
+    _check(getattr(lib(), "b200_msm_" + group)(_p(bases), _p(scalars), _sz(bases.shape[0]), _p(out)), "b200_msm_" + group)
+    return out
+
+
+def multi_exp_with_mixed_addition(group, bases, scalars, chunks: int = 1, method: int = multi_exp_method_BDLO12):
+    """multiexp.tcc:443-496 pre-filters scalars 0 and 1 on the CPU before calling multi_exp; on the
+    GPU zero digits are skipped and one-digits land in bucket 1, so both entry points share a kernel."""
+    return multi_exp(group, bases, scalars, chunks, method)
+
+
+def sum_partials(group, pts):
+    """Host-side sum of per-GPU / per-rank partial results (multiexp.tcc:433-438); normalised."""
+    L = _LIMBS[group]
+    pts = _arr(pts, L)
+    out = np.zeros(L, dtype=np.uint64)
+    _check(getattr(lib(), "b200_sum_partials_" + group)(_p(pts), _sz(pts.shape[0]), _p(out)), "b200_sum_partials")
+    return out
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Index range of `rank` when n points are split over `world` GPUs: [rank*floor(n/world), ...),
+    the last rank takes the remainder (multiexp.tcc:417-431)."""
+    if world <= 1 or n < world:
+        return (0, n) if rank == 0 else (n, n)
+    one = n // world
+    lo = rank * one
+    return (lo, n if rank == world - 1 else lo + one)
+
+
+class CommitmentKey:
+    """Device-resident bases (CommScheme's g1s / g2s, LS/prototools/commit.h:129-139)."""
+
+    def __init__(self, group, bases=None, device_affine_ptr=None, n=None):
+        self.group = group
+        h = ctypes.c_uint64(0)
+        if device_affine_ptr is not None:
+            self.n = int(n)
+            _check(getattr(lib(), "b200_pin_affine_dev_" + group)(_vp(device_affine_ptr), _sz(self.n), ctypes.byref(h)),
+                   "b200_pin_affine_dev_" + group)
+        else:
+            bases = _arr(bases, _LIMBS[group])
+            self.n = bases.shape[0]
+            _check(getattr(lib(), "b200_pin_bases_" + group)(_p(bases), _sz(self.n), ctypes.byref(h)), "b200_pin_bases_" + group)
+        self.handle = h.value
+
+    def multi_exp(self, scalars, offset: int = 0):
+        scalars = _arr(scalars, 4)
+        out = np.zeros(_LIMBS[self.group], dtype=np.uint64)
+        _check(getattr(lib(), "b200_msm_pinned_" + self.group)(ctypes.c_uint64(self.handle), _sz(offset), _p(scalars),
+                                                              _sz(scalars.shape[0]), _p(out)), "b200_msm_pinned")
+        return out
+
+    def multi_exp_device(self, d_scalars_ptr: int, n: int, offset: int = 0, stream: int = 0):
+        out = np.zeros(_LIMBS[self.group], dtype=np.uint64)
+        _check(getattr(lib(), "b200_msm_pinned_dev_" + self.group)(ctypes.c_uint64(self.handle), _sz(offset), _vp(d_scalars_ptr),
+                                                                  _sz(n), _vp(stream), _p(out)), "b200_msm_pinned_dev")
+        return out
+
+    def close(self):
+        if self.handle and _lib is not None:
+            _lib.b200_unpin_bases(ctypes.c_uint64(self.handle))
+        self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- fixed-base exponentiation (multiexp.hpp:96-124) -----------------------------------
+def get_exp_window_size(group, num_scalars: int) -> int:
+    """libff's tuned table (alt_bn128_init.cpp:157-201, 220-264); kept for API parity — the engine
+    picks its own window for the GPU table."""
+    return int(getattr(lib(), "b200_exp_window_size_" + group)(int(num_scalars)))
+
+
+class WindowTable:
+    """Stands in for libff::window_table<T>: a handle to an affine table in HBM."""
+
+    def __init__(self, group, g, expected_scalars: int = 1 << 16):
+        self.group = group
+        g = _arr(g, _LIMBS[group])
+        h = ctypes.c_uint64(0)
+        _check(getattr(lib(), "b200_window_table_create_" + group)(_p(g), _sz(expected_scalars), ctypes.byref(h)),
+               "b200_window_table_create")
+        self.handle = h.value
+
+    def close(self):
+        if self.handle and _lib is not None:
+            _lib.b200_window_table_destroy(ctypes.c_uint64(self.handle))
+        self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def get_window_table(group, scalar_size: int, window: int, g, expected_scalars: int = 1 << 16) -> WindowTable:
+    """multiexp.tcc:547-583.  scalar_size/window are accepted for parity; no caller can observe the layout."""
+    return WindowTable(group, g, expected_scalars)
+
+
+def batch_exp(scalar_size: int, window: int, table: WindowTable, v):
+    """multiexp.tcc:614-646: [v_i * g]; normalised points (batch_to_special form)."""
+    return batch_exp_with_coeff(scalar_size, window, table, None, v)
+
+
+def batch_exp_with_coeff(scalar_size: int, window: int, table: WindowTable, coeff, v):
+    """multiexp.tcc:648-681: [(coeff * v_i) * g]."""
+    v = _arr(v, 4)
+    coeff = None if coeff is None else _arr(coeff, 4)
+    out = np.zeros((v.shape[0], _LIMBS[table.group]), dtype=np.uint64)
+    _check(getattr(lib(), "b200_batch_exp_table_" + table.group)(ctypes.c_uint64(table.handle), _p(v), _sz(v.shape[0]), _p(coeff),
+                                                                _p(out)), "b200_batch_exp_table")
+    return out
+
+
+def batch_exp_device(table: WindowTable, d_scalars_ptr: int, n: int, d_out_affine_ptr: int, stream: int = 0):
+    _check(getattr(lib(), "b200_batch_exp_table_dev_" + table.group)(ctypes.c_uint64(table.handle), _vp(d_scalars_ptr), _sz(n),
+                                                                    _vp(d_out_affine_ptr), _vp(stream)), "b200_batch_exp_table_dev")
+
+
+def batch_exp_once(group, g, v, coeff=None):
+    """get_window_table + batch_exp in one call (LS/utils/util.h:119-134 simpleBatchExp)."""
+    g, v = _arr(g, _LIMBS[group]), _arr(v, 4)
+    coeff = None if coeff is None else _arr(coeff, 4)
+    out = np.zeros((v.shape[0], _LIMBS[group]), dtype=np.uint64)
+    _check(getattr(lib(), "b200_batch_exp_" + group)(_p(g), _p(v), _sz(v.shape[0]), _p(coeff), _p(out)), "b200_batch_exp")
+    return out
+
+
+def batch_to_special(group, vec):
+    """multiexp.tcc:683-715: every point to (X/Z^2, Y/Z^3, 1); zeros to the group's zero."""
+    vec = _arr(vec, _LIMBS[group]).copy()
+    _check(getattr(lib(), "b200_batch_to_affine_" + group)(_p(vec), _sz(vec.shape[0])), "b200_batch_to_affine")
+    return vec
+
+
+# ---- introspection ---------------------------------------------------------------------
+def last_stats() -> dict:
+    s = Stats()
+    lib().b200_last_stats(ctypes.byref(s))
+    return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def set_tuning(window_bits: int = 0, chunk_len: int = 0):
+    _check(lib().b200_set_tuning(int(window_bits), int(chunk_len)), "b200_set_tuning")
+
+
+def imad_peak(kind: int = 0, iters: int = 4096):
+    ops = ctypes.c_double(0)
+    ms = ctypes.c_double(0)
+    _check(lib().b200_imad_peak(int(kind), int(iters), ctypes.byref(ops), ctypes.byref(ms)), "b200_imad_peak")
+    return ops.value, ms.value
+
+
+def test_field_op(field: int, op: int, a, b=None):
+    W = 8 if field == 2 else 4
+    a = _arr(a, W)
+    b = None if b is None else _arr(b, W)
+    out = np.zeros_like(a)
+    _check(lib().b200_test_field_op(int(field), int(op), _p(a), _p(b), _sz(a.shape[0]), _p(out)), "b200_test_field_op")
+    return out
+
+
+def test_group_op(group: int, op: int, a, b=None, k: int = 0):
+    L = 12 if group == 0 else 24
+    a = _arr(a, L)
+    b = None if b is None else _arr(b, L)
+    out = np.zeros_like(a)
+    _check(lib().b200_test_group_op(int(group), int(op), _p(a), _p(b), _sz(a.shape[0]), ctypes.c_uint32(k), _p(out)),
+           "b200_test_group_op")
+    return out

@@ -1,0 +1,194 @@
+// engine_common.hpp — state and plumbing shared by the three translation units of
+// libb200msm.so (engine_core.cu: C-ABI + lifecycle; engine_g1.cu / engine_g2.cu:
+// the per-group instantiations of engine_impl.cuh).  Split so the groups compile
+// in parallel.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200_msm.h"
+
+namespace b200 {
+namespace eng {
+
+
+// ------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------
+extern std::mutex g_mu;
+extern std::string g_err;
+int fail(int code, const char *fmt, ...);
+
+struct CudaError {
+    std::string msg;
+};
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            char b__[512];                                                                                    \
+            snprintf(b__, sizeof b__, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            throw CudaError{b__};                                                                             \
+        }                                                                                                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------
+// device context
+// ------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(256, bytes + bytes / 8);
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Device {
+    int id = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    // inputs
+    DevBuf scalars, bases_jac, bases_aff, flags, prefix;
+    // sort
+    DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, meta, order, len_hist, len_cursor;
+    // accumulation / reduction
+    DevBuf partial, block_out, window_sums;
+    // batch_exp
+    DevBuf out_jac, out_norm, coeff;
+    void *h_pinned = nullptr;  // small pinned staging (window sums, totals)
+    size_t h_pinned_cap = 0;
+    uint32_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] whole pipeline, [2,3] k_accumulate
+
+    void ensure_pinned(size_t bytes)
+    {
+        if (bytes <= h_pinned_cap) return;
+        if (h_pinned) CK(cudaFreeHost(h_pinned));
+        h_pinned = nullptr;
+        CK(cudaHostAlloc(&h_pinned, bytes, cudaHostAllocDefault));
+        h_pinned_cap = bytes;
+    }
+    void release()
+    {
+        cudaSetDevice(id);
+        DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
+                         &entries, &meta, &order, &len_hist, &len_cursor, &partial, &block_out, &window_sums, &out_jac,
+                         &out_norm, &coeff};
+        for (DevBuf *b : all) b->release();
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        h_pinned_cap = 0;
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        for (auto &e : ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+    }
+};
+
+struct Shard {
+    int dev;  // index into g_devs
+    size_t begin, count;
+    void *d_aff = nullptr;      // Affine<F>[count]
+    uint8_t *d_flags = nullptr; // count
+};
+
+struct PinnedBases {
+    int group;  // 0 G1, 1 G2
+    size_t n;
+    std::vector<Shard> shards;
+};
+
+struct WindowTable {
+    int group;
+    uint32_t w, rows;
+    std::vector<void *> d_table;  // per device: Affine<F>[rows << w]
+};
+
+
+extern std::vector<Device> g_devs;
+extern bool g_init;
+extern std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
+extern std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
+extern uint64_t g_next_handle;
+extern b200_stats_t g_stats;
+extern int g_tune_c, g_tune_L;
+
+inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+#define LAUNCH(D, kernel, grid, block, smem, st, ...)             \
+    do {                                                          \
+        kernel<<<grid, block, smem, st>>>(__VA_ARGS__);           \
+        (D).launches++;                                           \
+        CK(cudaGetLastError());                                   \
+    } while (0)
+
+std::vector<std::pair<size_t, size_t>> split_range(size_t n, size_t parts);
+
+template <class Fn>
+void for_each_shard(size_t nshards, Fn fn)
+{
+    if (nshards == 1) {
+        fn(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(nshards);
+    for (size_t i = 0; i < nshards; i++)
+        th.emplace_back([&, i] {
+            try {
+                fn(i);
+            } catch (const CudaError &e) {
+                errs[i] = e.msg;
+            }
+        });
+    for (auto &t : th) t.join();
+    for (auto &e : errs)
+        if (!e.empty()) throw CudaError{e};
+}
+
+// per-group entry points: templates defined in engine_impl.cuh, explicitly
+// instantiated for Fq in engine_g1.cu and for Fq2 in engine_g2.cu
+template <class F> int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out);
+template <class F> int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *handle);
+template <class F> int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const void *d_scalars, size_t n,
+                                  void *stream, uint64_t *out);
+template <class F> int table_create(const uint64_t *base, size_t expected, uint64_t *handle);
+template <class F> int batch_exp_table(uint64_t handle, const uint64_t *scalars, const void *d_scalars, size_t n,
+                                       const uint64_t *coeff, uint64_t *out, void *d_out_affine, void *stream);
+template <class F> int batch_exp_once(const uint64_t *base, const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out);
+template <class F> int batch_to_affine(uint64_t *pts, size_t n);
+template <class F> int test_group_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint32_t k, uint64_t *out);
+int test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);  // engine_g1.cu
+
+}  // namespace eng
+}  // namespace b200

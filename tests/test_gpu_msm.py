@@ -1,0 +1,115 @@
+"""GPU: multi_exp / multi_exp_with_mixed_addition through the C-ABI, bit-exact (after
+affine normalisation) against the reference fixtures, the oracle at sizes it finishes in
+seconds, and the scalar-sum identity of SURVEY.md §8(c) at full benchmark sizes."""
+import numpy as np
+import pytest
+
+from oracle.binding import R_ORDER, ints_to_mont, limbs_to_int, MONT_R
+from tests import inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_golden_cases(engine, golden, grp):
+    g = golden(f"msm_{grp}")
+    for name in g["names"]:
+        B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
+        assert (engine.multi_exp(grp, B, S) == R).all(), (grp, name)
+        assert (engine.multi_exp_with_mixed_addition(grp, B, S, chunks=8) == R).all(), (grp, name)
+
+
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_golden_cases_forced_geometry(engine, golden, grp):
+    """Small windows / tiny task length force multi-task buckets, the warp combine and the
+    segment weighting paths on the same fixtures."""
+    g = golden(f"msm_{grp}")
+    try:
+        for c, L in ((2, 1), (3, 2), (5, 3), (8, 4), (13, 7)):
+            engine.set_tuning(c, L)
+            for name in g["names"]:
+                B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
+                assert (engine.multi_exp(grp, B, S) == R).all(), (grp, name, c, L)
+    finally:
+        engine.set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("grp,n", [("g1", 1 << 12), ("g1", (1 << 14) + 7), ("g2", 1 << 10)])
+def test_uniform_vs_oracle(engine, orc, grp, n):
+    P, k = inputs.bases(orc, grp, n, seed=301)
+    s = inputs.fr_uniform(orc, n, seed=302)
+    want = orc.msm(grp, P, s, chunks=orc.max_threads())
+    assert (engine.multi_exp(grp, P, s) == want).all()
+    assert (inputs.scalar_sum_check(orc, grp, k, s) == want).all()
+
+
+@pytest.mark.parametrize("grp,n", [("g1", 3000), ("g2", 700)])
+def test_distributions_vs_oracle(engine, orc, grp, n):
+    P, _ = inputs.bases(orc, grp, n, seed=311)
+    PJ, _ = inputs.bases(orc, grp, n, seed=312, affine=False)  # callers pass Z != 1 (cplink.cc:56)
+    cases = {
+        "jacobian": (PJ, inputs.fr_uniform(orc, n, seed=313)),
+        "32bit": (P, inputs.fr_small(n, 32)),
+        "zero_one_heavy": (P, inputs.fr_zero_one_heavy(orc, n)),
+        "all_equal_bases": (np.tile(PJ[3], (n, 1)), inputs.fr_uniform(orc, n, seed=314)),
+        "all_ones": (P, inputs.fr_const(n, 1)),
+        "hot_bucket": (P, inputs.fr_const(n, 0xabcdef)),
+    }
+    for name, (B, S) in cases.items():
+        assert (engine.multi_exp(grp, B, S) == orc.msm(grp, B, S, chunks=orc.max_threads(), variant=1)).all(), name
+
+
+def test_cplink_shape_prove(engine, orc):
+    """cplink prove: one G1 MSM, n = 1026, Jacobian bases (LS/gadgets/subspace.cc:78-85)."""
+    n = 1026
+    P, _ = inputs.bases(orc, "g1", n, seed=321, affine=False)
+    w = inputs.fr_uniform(orc, n, seed=322)
+    assert (engine.multi_exp_with_mixed_addition("g1", P, w) == orc.msm("g1", P, w, variant=1)).all()
+
+
+@pytest.mark.parametrize("grp,n", [("g1", 5000), ("g2", 600)])
+def test_pinned_key_prefixes(engine, orc, grp, n):
+    """CPPoly::prove runs MSMs over prefixes of one key (LS/gadgets/poly.h:77-88)."""
+    P, _ = inputs.bases(orc, grp, n, seed=331, affine=False)
+    key = engine.CommitmentKey(grp, P)
+    try:
+        for m in (n, n // 2, n // 4, 1, 0):
+            s = inputs.fr_uniform(orc, m, seed=332 + m)
+            assert (key.multi_exp(s) == orc.msm(grp, P[:m], s, chunks=orc.max_threads())).all(), m
+        s = inputs.fr_uniform(orc, 100, seed=340)
+        assert (key.multi_exp(s, offset=37) == orc.msm(grp, P[37:137], s)).all()
+    finally:
+        key.close()
+
+
+def _scalar_sum_expected(orc, grp, k, s):
+    """(sum s_i k_i mod r) * G, with the big-integer sum vectorised over 64-bit limbs."""
+    rinv = pow(MONT_R, -1, R_ORDER)
+
+    def to_ints(a):
+        a = np.asarray(a, dtype=np.uint64)
+        return [((int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192) * rinv) % R_ORDER for r in a]
+
+    tot = sum(x * y for x, y in zip(to_ints(k), to_ints(s))) % R_ORDER
+    return orc.scalar_mul(grp, orc.one(grp), ints_to_mont([tot], R_ORDER), normalise=True)[0]
+
+
+@pytest.mark.parametrize("grp,log2n", [("g1", 18), ("g1", 20), ("g2", 16)])
+def test_scalar_sum_identity_at_scale(engine, orc, grp, log2n):
+    """sum s_i (k_i G) == (sum s_i k_i) G at BASELINE.json sizes; bases made by the GPU fixed-base path
+    and spot-checked against the oracle."""
+    n = 1 << log2n
+    k = inputs.fr_uniform(orc, n, seed=401)
+    s = inputs.fr_uniform(orc, n, seed=402)
+    table = engine.get_window_table(grp, 254, 0, orc.one(grp), expected_scalars=n)
+    P = engine.batch_exp(254, 0, table, k)
+    table.close()
+    idx = np.r_[0:64, n - 64:n, np.random.default_rng(1).integers(0, n, 256)]
+    assert (P[idx] == orc.batch_exp(grp, orc.one(grp), k[idx])).all()
+    want = _scalar_sum_expected(orc, grp, k, s)
+    assert (engine.multi_exp(grp, P, s) == want).all()
+    key = engine.CommitmentKey(grp, P)
+    assert (key.multi_exp(s) == want).all()
+    key.close()
+    st = engine.last_stats()
+    assert st["n"] == n and st["kernel_launches"] >= 10
