@@ -83,7 +83,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -169,7 +169,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=20, help="points per GPU = 2^log2n")
@@ -310,7 +310,9 @@ def main():
         "bound": "imad", "kernel": f"k_accumulate<{'Fq' if group == 'g1' else 'Fq2'}>",
         "achieved": achieved, "peak": imad_wide_peak / 1e12, "unit": "T multiply-add/s (32x32+64, lane-ops)",
         "frac": achieved / (imad_wide_peak / 1e12), "traffic": None,
-        "peak_source": "measured live: b200_imad_peak(IMAD.WIDE.U32), all SMs",
+        "peak_source": "measured live on this GPU: b200_imad_peak(0) = the IMAD.WIDE.U32[.X] carry-row stream of the "
+                       "Montgomery product on all SMs (hardware issue limit: 32 wide multiply-adds/clk/SM = "
+                       f"{32 * 148 * 1.965e9 / 1e12:.2f} T/s at 1965 MHz, ncu sm__pipe_fmaheavy_cycles_active)",
         "ms_per_launch": acc, "share_of_step": acc / (float(np.mean(res_ms))),
         "algorithmic": {"mixed_adds_per_launch": entries, "modmul_per_mixed_add": MODMUL_MIXED,
                         "imad_per_modmul": 136, "modmul_per_mixed_add_executed": MODMUL_ACTUAL},

@@ -158,10 +158,11 @@ typedef struct {
 int b200_last_stats(b200_stats_t *out);
 /* Overrides for tuning / tests: window bits c (0 = auto), chunk length L (0 = auto). */
 int b200_set_tuning(int window_bits, int chunk_len);
-/* IMAD roofline microbenchmark: runs `iters` rounds of independent
- * IMAD.WIDE.U32 chains on every SM of device 0 and returns multiply-adds
- * (lane-ops) per second.  kind: 0 IMAD.WIDE.U32 (32x32+64), 1 IMAD (32x32+32 lo),
- * 2 Montgomery multiplications per second (Fq::mul chains). */
+/* IMAD roofline microbenchmark on every SM of device 0; returns multiply-adds (lane-ops)
+ * per second.  kind 0: the 32x32+64 multiply-add stream of the Montgomery product
+ * (IMAD.WIDE.U32 / IMAD.WIDE.U32.X carry rows, 16 wide + 1 narrow per step; `iters` rounds
+ * of 4 steps per thread) — the denominator of the IMAD roofline; kind 1: IMAD (32x32+32
+ * low half), 8 chains; kind 2: Montgomery multiplications per second (Fq::mul chains). */
 int b200_imad_peak(int kind, int iters, double *ops_per_sec, double *elapsed_ms);
 
 #ifdef __cplusplus

@@ -1,0 +1,101 @@
+// cplink_driver.cc — timed CPlink run over the reference's own classes (BASELINE.json
+// configs[0], "cplink prove ms").  Same protocol flow as LS/examples/cplink.cc:79-117
+// (LS = /root/reference/src): Pedersen commitments to one vector u under two bases, a
+// linking relation [h | g1s ; f] and SubspaceSnark keygen / prove / verify — but with the
+// size on the command line and a timer around every phase; the shipped example has N = 2^10
+// fixed and prints nothing.  Built twice by integration/Makefile from the SAME file: against
+// the reference's libff headers (cplink_cpu) and with legosnark_b200/shim ahead of them
+// (cplink_b200); nothing else differs.
+//
+//   cplink_{cpu,b200} [log2N = 10] [prove repetitions = 3]
+// prints one JSON line; exit code 0 iff the proof verifies.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+using namespace std;
+
+#include "subspace.h"
+#include "util.h"
+
+#include "harness.h"
+using harness::now_ms;
+
+int main(int argc, char **argv)
+{
+    const int log2n = argc > 1 ? atoi(argv[1]) : 10;
+    const int reps = argc > 2 ? atoi(argv[2]) : 3;
+    const size_t N = (size_t)1 << log2n;
+    libff::inhibit_profiling_info = true;
+    libff::inhibit_profiling_counters = true;
+    default_ec_pp::init_public_params();
+
+    double t0 = now_ms();
+    CommScheme ped;
+    ped.keygen((long)N);
+    // the second basis: f_0 (hiding) and f_1..f_N, random multiples of the generator
+    const vector<LFr> fk = harness::scalars<LFr>(N + 1, 1);
+#ifdef B200_SHIM_MULTIEXP_HPP_
+    vector<LG1> F = cputil::simpleBatchExp<LG1, LFr>(LG1::one(), fk);  // LS/utils/util.h:119-134 -> batch_exp
+#else
+    vector<LG1> F(N + 1);
+    for (size_t i = 0; i <= N; i++) F[i] = fk[i] * LG1::one();  // cplink.cc:51-58
+#endif
+    const double setup_ms = now_ms() - t0;
+
+    // relation x = M w with w = (r_H, r_F, u):   row 0 = [h, 0, g1s],  row 1 = [0, f_0, f_1..f_N]
+    SubspaceRel rel;
+    rel.withNRows(2).withNCols((int)(2 * F.size())).withoutScalars();
+    vector<ColG1> M(2 * F.size());
+    M[0].push_back(CoeffPos<LG1>(ped.getBlindingH(), 0));
+    const vector<LG1> g1s = ped.getBases1();
+    for (size_t i = 0; i < g1s.size(); i++) M[2 + i].push_back(CoeffPos<LG1>(g1s[i], 0));
+    for (size_t i = 0; i < F.size(); i++) M[1 + i].push_back(CoeffPos<LG1>(F[i], 1));
+    rel.withMatrix(M);
+
+    const vector<LFr> u = harness::scalars<LFr>(N, 2);
+
+    t0 = now_ms();
+    auto cm = ped.commit(u);  // G1 MSM + G2 MSM, LS/prototools/commit.h:149-158
+    const LG1 cH = cm.c.c;
+    const LFr rH = cm.r;
+    const LFr rF = harness::scalars<LFr>(1, 3)[0];
+    const vector<LG1> Frest(F.begin() + 1, F.end());
+    const LG1 cF = multiExpMA<LG1>(Frest, u) + rF * F[0];
+    const double commit_ms = now_ms() - t0;
+
+    vector<LFr> w({rH, rF});
+    w.insert(w.end(), u.begin(), u.end());
+
+    SubspaceSnark snark;
+    t0 = now_ms();
+    auto crs = snark.keygen(&rel);  // LS/gadgets/subspace.cc:37-76
+    const double keygen_ms = now_ms() - t0;
+
+    vector<double> prove_ms;
+    SubspacePf *pf = nullptr;
+    for (int r = 0; r < reps; r++) {
+        t0 = now_ms();
+        pf = snark.prove(crs, w);  // one G1 MSM, LS/gadgets/subspace.cc:78-85
+        prove_ms.push_back(now_ms() - t0);
+    }
+    t0 = now_ms();
+    const bool ok = snark.verify(crs, {cH, cF}, pf);  // pairings on the host, subspace.cc:106-133
+    const double verify_ms = now_ms() - t0;
+
+    harness::Fingerprint fp;
+    fp.point(cH);
+    fp.point(cm.c.kc);
+    fp.point(cF);  // the CRS (and with it the proof) is drawn from std::random_device inside keygen: not fingerprinted
+    double best = prove_ms[0];
+    for (double x : prove_ms) best = x < best ? x : best;
+    printf("{\"example\": \"cplink\", \"impl\": \"%s\", \"log2N\": %d, \"prove_points\": %zu, \"setup_ms\": %.3f, "
+           "\"commit_ms\": %.3f, \"keygen_ms\": %.3f, \"prove_ms_first\": %.3f, \"prove_ms_best\": %.3f, "
+           "\"verify_ms\": %.3f, \"verified\": %s, \"fingerprint\": \"%s\"}\n",
+#ifdef B200_SHIM_MULTIEXP_HPP_
+           "b200",
+#else
+           "libff-cpu",
+#endif
+           log2n, w.size(), setup_ms, commit_ms, keygen_ms, prove_ms[0], best, verify_ms, ok ? "true" : "false", fp.hex().c_str());
+    return ok ? 0 : 1;
+}

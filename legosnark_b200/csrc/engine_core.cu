@@ -358,7 +358,7 @@ int b200_imad_peak(int kind, int iters, double *ops_per_sec, double *elapsed_ms)
         CK(cudaEventElapsedTime(&ms, e0, e1));
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
-        const double per_thread = kind == 2 ? 2.0 * iters : 8.0 * iters;
+        const double per_thread = kind == 2 ? 2.0 * iters : kind == 0 ? 4.0 * 17.0 * iters : 8.0 * iters;
         *ops_per_sec = per_thread * blocks * threads / (ms * 1e-3);
         if (elapsed_ms) *elapsed_ms = ms;
         return B200_OK;

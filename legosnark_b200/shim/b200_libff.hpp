@@ -1,0 +1,153 @@
+// b200_libff.hpp — C++ host side of the drop-in: libff group / field objects <-> the
+// C-ABI of include/b200_msm.h.
+//
+// The reference has no FFI; its boundary is the set of function templates in
+//   LFF/algebra/scalar_multiplication/multiexp.hpp:56-127
+// (LFF = depends/libsnark/depends/libff/libff) instantiated in the caller's TU.  The
+// shadow header shim/libff/algebra/scalar_multiplication/multiexp.hpp keeps those
+// templates' names and signatures and forwards the four concrete groups
+//   alt_bn128_G1 / alt_bn128_G2  (LFF/algebra/curves/alt_bn128/alt_bn128_g1.hpp:35, _g2.hpp:36)
+//   bn128_G1     / bn128_G2      (LFF/algebra/curves/bn128/bn128_g1.hpp:36, bn128_g2.hpp:37)
+// with FieldT == T::scalar_field to the functions below.  Every other T (e.g. libsnark's
+// knowledge_commitment<T1,T2>) keeps the reference's template.
+//
+// The in-memory images are passed as they are: a point is 3 (G1) or 6 (G2) Montgomery
+// field elements of 4 x u64 limbs, R = 2^256, Jacobian X|Y|Z, for both curve flavours
+// (identical limbs).  Failure of the engine (no CUDA device, CUDA
+// error) throws std::runtime_error: there is no CPU fallback behind this header.
+#ifndef B200_LIBFF_HPP_
+#define B200_LIBFF_HPP_
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "b200_msm.h"
+
+namespace libff {
+class alt_bn128_G1;
+class alt_bn128_G2;
+class bn128_G1;
+class bn128_G2;
+}  // namespace libff
+
+namespace b200shim {
+
+template <typename T>
+struct group_traits {
+    static const bool supported = false;
+};
+template <>
+struct group_traits<libff::alt_bn128_G1> {
+    static const bool supported = true;
+    static const int group = 0;
+    static const size_t limbs = 12;
+};
+template <>
+struct group_traits<libff::bn128_G1> {
+    static const bool supported = true;
+    static const int group = 0;
+    static const size_t limbs = 12;
+};
+template <>
+struct group_traits<libff::alt_bn128_G2> {
+    static const bool supported = true;
+    static const int group = 1;
+    static const size_t limbs = 24;
+};
+template <>
+struct group_traits<libff::bn128_G2> {
+    static const bool supported = true;
+    static const int group = 1;
+    static const size_t limbs = 24;
+};
+
+inline void check(int rc, const char *what)
+{
+    if (rc != B200_OK) throw std::runtime_error(std::string(what) + " failed: " + b200_last_error());
+}
+
+// One engine per process, created on first use.  B200_GPUS=<n> limits the devices an MSM is
+// sharded over (default: all visible), mirroring OMP_NUM_THREADS for the reference's chunks.
+inline void ensure_init()
+{
+    static const bool once = [] {
+        const char *e = std::getenv("B200_GPUS");
+        check(b200_init(e ? std::atoi(e) : 0), "b200_init");
+        return true;
+    }();
+    (void)once;
+}
+
+template <typename T>
+inline const uint64_t *limbs_of(const T *p)
+{
+    static_assert(sizeof(T) == group_traits<T>::limbs * 8, "unexpected point layout");
+    return reinterpret_cast<const uint64_t *>(p);
+}
+
+// engine output (x, y, 1) / (0, 1, 0)  ->  T; the zero is written as the curve's own
+// T::zero() (alt_bn128: (0,1,0), alt_bn128_init.cpp:145-147; bn128: (1,1,0), bn128_init.cpp:101-103)
+template <typename T>
+inline T point_from_limbs(const uint64_t *l)
+{
+    const size_t L = group_traits<T>::limbs, zoff = 2 * L / 3;
+    uint64_t z = 0;
+    for (size_t i = zoff; i < L; i++) z |= l[i];
+    if (z == 0) return T::zero();
+    T r;
+    std::memcpy(reinterpret_cast<void *>(&r), l, L * 8);
+    return r;
+}
+
+template <typename T, typename FieldT>
+inline T msm(const T *bases, const FieldT *scalars, size_t n)
+{
+    static_assert(std::is_same<FieldT, typename T::scalar_field>::value, "scalars must be the group's Fr");
+    static_assert(sizeof(FieldT) == 32, "unexpected scalar layout");
+    ensure_init();
+    uint64_t out[24];
+    const uint64_t *b = n ? limbs_of(bases) : nullptr;
+    const uint64_t *s = n ? reinterpret_cast<const uint64_t *>(scalars) : nullptr;
+    if (group_traits<T>::group == 0) check(b200_msm_g1(b, s, n, out), "b200_msm_g1");
+    else check(b200_msm_g2(b, s, n, out), "b200_msm_g2");
+    return point_from_limbs<T>(out);
+}
+
+template <typename T, typename FieldT>
+inline std::vector<T> fixed_base_exp(const T &base, const std::vector<FieldT> &v, const FieldT *coeff)
+{
+    static_assert(std::is_same<FieldT, typename T::scalar_field>::value, "scalars must be the group's Fr");
+    ensure_init();
+    const size_t L = group_traits<T>::limbs, n = v.size();
+    std::vector<T> res(n, T::zero());
+    if (n == 0) return res;
+    std::vector<uint64_t> out(n * L);
+    const uint64_t *s = reinterpret_cast<const uint64_t *>(v.data());
+    const uint64_t *c = coeff ? reinterpret_cast<const uint64_t *>(coeff) : nullptr;
+    if (group_traits<T>::group == 0) check(b200_batch_exp_g1(limbs_of(&base), s, n, c, out.data()), "b200_batch_exp_g1");
+    else check(b200_batch_exp_g2(limbs_of(&base), s, n, c, out.data()), "b200_batch_exp_g2");
+    for (size_t i = 0; i < n; i++) res[i] = point_from_limbs<T>(out.data() + i * L);
+    return res;
+}
+
+template <typename T>
+inline void to_special(std::vector<T> &vec)
+{
+    ensure_init();
+    const size_t L = group_traits<T>::limbs, n = vec.size();
+    if (n == 0) return;
+    std::vector<uint64_t> buf(n * L);
+    std::memcpy(buf.data(), limbs_of(vec.data()), n * L * 8);
+    if (group_traits<T>::group == 0) check(b200_batch_to_affine_g1(buf.data(), n), "b200_batch_to_affine_g1");
+    else check(b200_batch_to_affine_g2(buf.data(), n), "b200_batch_to_affine_g2");
+    for (size_t i = 0; i < n; i++) vec[i] = point_from_limbs<T>(buf.data() + i * L);
+}
+
+}  // namespace b200shim
+#endif  // B200_LIBFF_HPP_
