@@ -80,7 +80,7 @@ struct Device {
     // sort
     DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, meta, order, len_hist, len_cursor;
     // accumulation / reduction
-    DevBuf partial, block_out, window_sums;
+    DevBuf partial, seg_run, seg_acc, job_out, split, done, window_sums;
     // batch_exp
     DevBuf out_jac, out_norm, coeff;
     void *h_pinned = nullptr;  // small pinned staging (window sums, totals)
@@ -100,7 +100,7 @@ struct Device {
     {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
-                         &entries, &meta, &order, &len_hist, &len_cursor, &partial, &block_out, &window_sums, &out_jac,
+                         &entries, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &out_jac,
                          &out_norm, &coeff};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);

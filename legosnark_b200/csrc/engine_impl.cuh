@@ -19,10 +19,17 @@ inline MsmGeom choose_geometry(size_t n)
     if (g_tune_c > 0) {
         best_c = (uint32_t)std::min(std::max(g_tune_c, 2), 24);
     } else {
+        // Time model fitted to B200 measurements (profiles/, DESIGN.md "window choice"), in ms:
+        // bucket sort + accumulation are linear in the W * n entries; the window reduction costs
+        // 2 XYZZ additions per bucket but never less than its serial depth; the last stage is
+        // pure latency.
         double best = 1e300;
         for (uint32_t c = 4; c <= 22; c++) {
-            const double W = std::ceil(255.0 / c);
-            const double cost = W * ((double)n * 10.0 + (double)(1u << (c - 1)) * 40.0);
+            const double W = std::ceil(255.0 / c), B = (double)(1u << (c - 1));
+            const double entries = W * (double)n;
+            const double acc = std::max(entries * 1.7e-7, 0.15 + entries * 0.5e-7);
+            const double red = std::max(W * B * 5.4e-7, 0.16) + 0.25;
+            const double cost = acc + red;
             if (cost < best) {
                 best = cost;
                 best_c = c;
@@ -102,9 +109,13 @@ MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const ui
     if (max_entries >= (1ull << 32)) throw CudaError{"MSM shard too large: W * n must stay below 2^32 entries"};
     const size_t max_tasks = max_entries / g.L + g.NB;
     const uint32_t ntiles = cdiv(g.NB, SCAN_TILE);
-    const uint32_t S = std::min<uint32_t>(8, g.B);
-    const uint32_t nseg = cdiv(g.B, S);
-    const uint32_t nblk = cdiv(nseg, RED_THREADS);
+    // window reduction geometry: segments of S = 2^logS buckets, M segments per window
+    uint32_t logS = 3;
+    while ((1u << logS) > g.B) logS--;
+    const uint32_t M = g.B >> logS;
+    uint32_t njobs = 1;
+    while ((1u << (njobs - 1)) < M) njobs++;  // job 0 + one job per bit of the segment index
+    const size_t nseg = (size_t)g.W * M;
 
     D.cnt.ensure((size_t)g.NB * 4);
     D.off.ensure((size_t)g.NB * 4);
@@ -118,7 +129,14 @@ MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const ui
     D.len_hist.ensure((size_t)(g.L + 1) * 4);
     D.len_cursor.ensure((size_t)(g.L + 1) * 4);
     D.partial.ensure(max_tasks * sizeof(XYZZ<F>));
-    D.block_out.ensure((size_t)g.W * nblk * sizeof(XYZZ<F>));
+    D.seg_run.ensure(nseg * sizeof(XYZZ<F>));
+    D.seg_acc.ensure(nseg * sizeof(XYZZ<F>));
+    D.job_out.ensure((size_t)g.W * (njobs + 1) * RED2_SPLIT * sizeof(XYZZ<F>));
+    D.split.ensure(std::min<size_t>(g.NB, max_tasks) * 4 + 4);
+    if (D.done.cap < (size_t)g.W * 4) {
+        D.done.ensure(1024 * 4);
+        CK(cudaMemsetAsync(D.done.p, 0, D.done.cap, st));  // k_reduce_bits leaves the counters at zero
+    }
     D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
     D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
 
@@ -129,7 +147,8 @@ MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const ui
     uint32_t *toff = D.toff.as<uint32_t>(), *totals = D.totals.as<uint32_t>(), *entries = D.entries.as<uint32_t>();
     uint2 *tile_sums = D.tile_sums.as<uint2>(), *meta = D.meta.as<uint2>();
     uint32_t *order = D.order.as<uint32_t>(), *len_hist = D.len_hist.as<uint32_t>(), *len_cursor = D.len_cursor.as<uint32_t>();
-    XYZZ<F> *partial = D.partial.as<XYZZ<F>>(), *block_out = D.block_out.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
+    XYZZ<F> *partial = D.partial.as<XYZZ<F>>(), *seg_run = D.seg_run.as<XYZZ<F>>(), *seg_acc = D.seg_acc.as<XYZZ<F>>(),
+            *job_out = D.job_out.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
 
     const uint32_t pblocks = cdiv(n, 256);
     CK(cudaEventRecord(D.ev[0], st));
@@ -139,15 +158,17 @@ MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const ui
     LAUNCH(D, k_scan_apply, ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
     LAUNCH(D, k_digit_scatter, pblocks, 256, 0, st, d_scalars, d_flags, n, g, cursor, entries);
     const uint32_t tblocks = cdiv(max_tasks, 256);
-    LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist);
+    uint32_t *split = D.split.as<uint32_t>();
+    LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist, split);
     LAUNCH(D, k_len_scan, 1, 1024, 0, st, len_hist, len_cursor, g.L);
     LAUNCH(D, k_task_order, tblocks, 256, 2 * (g.L + 1) * 4, st, meta, totals, g, len_cursor, order);
     CK(cudaEventRecord(D.ev[2], st));
     LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
     CK(cudaEventRecord(D.ev[3], st));
-    LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 4, 128, 0, st, cnt, toff, g, partial);
-    LAUNCH(D, (k_window_reduce1<F>), dim3(nblk, g.W), RED_THREADS, 0, st, cnt, toff, partial, g, S, block_out);
-    LAUNCH(D, (k_window_reduce2<F>), g.W, 32, 0, st, block_out, nblk, wsums);
+    LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 8, 128, 0, st, cnt, toff, split, totals, g, partial);
+    LAUNCH(D, (k_reduce_segments<F>), cdiv(nseg, RED_THREADS), RED_THREADS, 0, st, cnt, toff, partial, g, logS, seg_run, seg_acc);
+    LAUNCH(D, (k_reduce_bits<F>), dim3((njobs + 1) * RED2_SPLIT, g.W), RED2_THREADS, 0, st, seg_run, seg_acc, M, logS, job_out, D.done.as<uint32_t>(),
+           wsums);
     CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.W * sizeof(XYZZ<F>), totals, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(D.ev[1], st));

@@ -248,6 +248,7 @@ static __global__ void __launch_bounds__(1024) k_scan_tiles(uint2 *__restrict__ 
     if (threadIdx.x == 0) {
         totals[0] = carry_sm.x;  // total entries
         totals[1] = carry_sm.y;  // total tasks
+        totals[2] = 0;           // number of split buckets (filled by k_task_meta)
     }
 }
 
@@ -316,8 +317,9 @@ __device__ __forceinline__ uint32_t bucket_of_task(const uint32_t *__restrict__ 
 }
 
 static __global__ void __launch_bounds__(256) k_task_meta(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off,
-                                                    const uint32_t *__restrict__ toff, const uint32_t *__restrict__ totals,
-                                                    MsmGeom g, uint2 *__restrict__ meta, uint32_t *__restrict__ len_hist)
+                                                    const uint32_t *__restrict__ toff, uint32_t *__restrict__ totals,
+                                                    MsmGeom g, uint2 *__restrict__ meta, uint32_t *__restrict__ len_hist,
+                                                    uint32_t *__restrict__ split)
 {
     extern __shared__ uint32_t sh_hist[];  // L + 1 bins
     for (uint32_t k = threadIdx.x; k <= g.L; k += blockDim.x) sh_hist[k] = 0;
@@ -331,6 +333,7 @@ static __global__ void __launch_bounds__(256) k_task_meta(const uint32_t *__rest
         const uint32_t len = rem < g.L ? rem : g.L;
         meta[t] = make_uint2(off[b] + j * g.L, len);
         atomicAdd(&sh_hist[len], 1u);
+        if (j == 0 && cnt[b] > g.L) split[atomicAdd(&totals[2], 1u)] = b;  // bucket spans several tasks
     }
     __syncthreads();
     for (uint32_t k = threadIdx.x; k <= g.L; k += blockDim.x)
@@ -434,104 +437,176 @@ __device__ __forceinline__ XYZZ<F> shfl_down_point(const XYZZ<F> &p, int delta)
 }
 
 template <class F>
-__device__ __forceinline__ XYZZ<F> warp_sum_point(XYZZ<F> v)
+__device__ __forceinline__ XYZZ<F> warp_sum_point(XYZZ<F> v, int width = 32)
 {
 #pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = width >> 1; o > 0; o >>= 1) {
         const XYZZ<F> other = shfl_down_point(v, o);
         xyzz_add_cold(&v, &other);
     }
     return v;  // lane 0 holds the sum
 }
 
-// buckets that were split into several tasks: one warp sums the partials into the first slot
+// buckets that were split into several tasks (listed by k_task_meta): their task partials are
+// summed into the bucket's first slot.  Four lanes serve one bucket (eight buckets per warp and
+// step: the common case is 2-3 partials, e.g. the short top window); buckets with more than 32
+// partials (a hot bucket: many equal scalars) are then served by the whole warp, one at a time.
+// With nothing split the kernel returns at once.
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_combine(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
+                                                         const uint32_t *__restrict__ split, const uint32_t *__restrict__ totals,
                                                          MsmGeom g, XYZZ<F> *__restrict__ partial)
 {
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nsplit = totals[2];
+    const uint32_t lane = threadIdx.x & 31, sub = lane >> 2, sl = lane & 3;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t b0 = warp * 32; b0 < g.NB; b0 += nwarps * 32) {
-        // each lane inspects one bucket; the warp then serves the split ones in turn
-        const uint32_t b = b0 + lane;
-        const uint32_t nt = b < g.NB ? tasks_of(cnt[b], g.L) : 0;
-        uint32_t pending = __ballot_sync(0xffffffffu, nt >= 2);
-        while (pending) {
-            const int src = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const uint32_t bb = b0 + src;
-            const uint32_t ntb = __shfl_sync(0xffffffffu, nt, src);
-            const uint32_t t0 = toff[bb];
-            XYZZ<F> acc = XYZZ<F>::inf();
-            for (uint32_t k = lane; k < ntb; k += 32) {
+    for (uint32_t base = warp * 8; base < nsplit; base += nwarps * 8) {
+        const uint32_t i = base + sub;
+        const bool live = i < nsplit;
+        const uint32_t b = live ? split[i] : 0u;
+        const uint32_t nt = live ? tasks_of(cnt[b], g.L) : 0u;
+        const uint32_t t0 = live ? toff[b] : 0u;
+        const bool big = nt > 32;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        if (!big)
+            for (uint32_t k = sl; k < nt; k += 4) {
                 const XYZZ<F> q = partial[t0 + k];
                 xyzz_add_cold(&acc, &q);
             }
-            acc = warp_sum_point(acc);
-            if (lane == 0) partial[t0] = acc;
+        {
+            XYZZ<F> other = shfl_down_point(acc, 2);
+            if (sl < 2) xyzz_add_cold(&acc, &other);
+            other = shfl_down_point(acc, 1);
+            if (sl == 0) xyzz_add_cold(&acc, &other);
+        }
+        if (live && !big && sl == 0) partial[t0] = acc;
+        uint32_t pending = __ballot_sync(0xffffffffu, big && sl == 0);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint32_t ntb = __shfl_sync(0xffffffffu, nt, src);
+            const uint32_t tb = __shfl_sync(0xffffffffu, t0, src);
+            XYZZ<F> wacc = XYZZ<F>::inf();
+            for (uint32_t k = lane; k < ntb; k += 32) {
+                const XYZZ<F> q = partial[tb + k];
+                xyzz_add_cold(&wacc, &q);
+            }
+            wacc = warp_sum_point(wacc);
+            if (lane == 0) partial[tb] = wacc;
             __syncwarp();
         }
     }
 }
 
 // ------------------------------------------------------------------------------
-// window reduction: W_k = sum_{j=1..B} j * bucket[k][j]
+// window reduction: R_k = sum_{j=0..B-1} (j + 1) * bucket[k][j]
+// (the running-sum loop of multiexp.tcc:244-278, restructured for parallelism)
+//
+// level 1  k_reduce_segments: one thread per segment of S = 2^logS consecutive buckets runs
+//          the classic running sum inside its segment:
+//              run_s = sum_t bucket[S s + t],   acc_s = sum_t (t + 1) bucket[S s + t]
+//          so that  R_k = sum_s acc_s + S * sum_s s * run_s.
+// level 2  k_reduce_bits: the second term by binary decomposition of s, which needs only
+//          plain sums (tree reductions, no serial chain over segments):
+//              sum_s s run_s = sum_b 2^b T_b,   T_b = sum_{s : bit b of s set} run_s.
+//          Block (job, part, k): job 0 sums the acc_s, job b + 1 sums T_b; each job is shared
+//          by RED2_SPLIT blocks, which double their partial sum b + logS times themselves (the
+//          doubling is linear); the last block of a window to finish adds all results into R_k.
 // ------------------------------------------------------------------------------
 constexpr int RED_THREADS = 128;
+constexpr int RED2_THREADS = 128;
 
-// block (x = block within window, y = window); thread = segment of S consecutive buckets
 template <class F>
-__global__ void __launch_bounds__(RED_THREADS) k_window_reduce1(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
-                                                                 const XYZZ<F> *__restrict__ partial, MsmGeom g, uint32_t S,
-                                                                 XYZZ<F> *__restrict__ block_out)
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_segments(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
+                                                                  const XYZZ<F> *__restrict__ partial, MsmGeom g, uint32_t logS,
+                                                                  XYZZ<F> *__restrict__ seg_run, XYZZ<F> *__restrict__ seg_acc)
 {
-    __shared__ XYZZ<F> sm[RED_THREADS / 32];
-    const uint32_t k = blockIdx.y;
-    const uint32_t seg = blockIdx.x * RED_THREADS + threadIdx.x;
-    const uint32_t j0 = seg * S;  // 0-based bucket index of the segment start; bucket j has weight j + 1
+    const uint32_t seg = blockIdx.x * RED_THREADS + threadIdx.x;  // global segment index over all windows
+    const uint32_t nseg = g.NB >> logS;
+    if (seg >= nseg) return;
+    const uint32_t b0 = seg << logS;  // segments never straddle windows: S divides B
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-    if (j0 < g.B) {
-        for (int jj = (int)S - 1; jj >= 0; jj--) {
-            const uint32_t j = j0 + (uint32_t)jj;
-            if (j < g.B) {
-                const uint32_t b = k * g.B + j;
-                if (cnt[b]) {
-                    const XYZZ<F> q = partial[toff[b]];
-                    xyzz_add_cold(&run, &q);
-                }
-            }
-            xyzz_add_cold(&acc, &run);
+    for (int t = (1 << logS) - 1; t >= 0; t--) {
+        const uint32_t b = b0 + (uint32_t)t;
+        if (cnt[b]) {
+            const XYZZ<F> q = partial[toff[b]];
+            xyzz_add_cold(&run, &q);
         }
-        // acc = sum (jj + 1) bucket[j0 + jj], run = sum bucket[j0 + jj]
-        if (j0) {
-            const XYZZ<F> wrun = xyzz_mul_small(run, j0);
-            xyzz_add_cold(&acc, &wrun);
-        }
+        xyzz_add_cold(&acc, &run);
     }
-    acc = warp_sum_point(acc);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        XYZZ<F> v = threadIdx.x < RED_THREADS / 32 ? sm[threadIdx.x] : XYZZ<F>::inf();
-        v = warp_sum_point(v);
-        if (threadIdx.x == 0) block_out[k * gridDim.x + blockIdx.x] = v;
-    }
+    seg_run[seg] = run;
+    seg_acc[seg] = acc;
 }
 
-// one warp per window sums the block results
 template <class F>
-__global__ void __launch_bounds__(32) k_window_reduce2(const XYZZ<F> *__restrict__ block_out, uint32_t nblk,
-                                                       XYZZ<F> *__restrict__ window_sums)
+__device__ __forceinline__ XYZZ<F> block_sum_point(XYZZ<F> v, XYZZ<F> *sm)
 {
-    const uint32_t k = blockIdx.x;
+    v = warp_sum_point(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : XYZZ<F>::inf();
+        v = warp_sum_point(v, (int)(blockDim.x >> 5));  // blockDim.x / 32 is a power of two
+    }
+    return v;  // thread 0 holds the block's sum
+}
+
+// grid ((njobs + 1) * RED2_SPLIT, W): job 0 sums twice as many points as the others and gets
+// twice the blocks; all blocks of a launch fit the machine in one wave (serial depth matters
+// here, not throughput: a point addition issued by a lone warp takes several microseconds)
+constexpr int RED2_SPLIT = 2;
+
+template <class F>
+__global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits(const XYZZ<F> *__restrict__ seg_run, const XYZZ<F> *__restrict__ seg_acc,
+                                                               uint32_t M, uint32_t logS, XYZZ<F> *__restrict__ job_out,
+                                                               uint32_t *__restrict__ done, XYZZ<F> *__restrict__ window_sums)
+{
+    __shared__ XYZZ<F> sm[RED2_THREADS / 32];
+    __shared__ uint32_t ticket;
+    const uint32_t nout = gridDim.x, k = blockIdx.y;
+    const uint32_t job = blockIdx.x < 2 * RED2_SPLIT ? 0 : blockIdx.x / RED2_SPLIT - 1;
+    const uint32_t nparts = job == 0 ? 2 * RED2_SPLIT : RED2_SPLIT;
+    const uint32_t part = job == 0 ? blockIdx.x : blockIdx.x % RED2_SPLIT;
+    const XYZZ<F> *src = (job == 0 ? seg_acc : seg_run) + (size_t)k * M;
+    // the segments this job sums: all of them (job 0) or those with bit (job - 1) set, enumerated
+    // densely so that every thread gets the same share
+    const uint32_t count = job == 0 ? M : M >> 1;
+    const uint32_t bit = job == 0 ? 0 : job - 1;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t i = threadIdx.x; i < nblk; i += 32) {
-        const XYZZ<F> q = block_out[k * nblk + i];
+    for (uint32_t i = part * RED2_THREADS + threadIdx.x; i < count; i += nparts * RED2_THREADS) {
+        const uint32_t s0 = job == 0 ? i : (((i >> bit) << (bit + 1)) | (1u << bit) | (i & ((1u << bit) - 1u)));
+        const XYZZ<F> q = src[s0];
         xyzz_add_cold(&acc, &q);
     }
-    acc = warp_sum_point(acc);
-    if (threadIdx.x == 0) window_sums[k] = acc;
+    acc = block_sum_point(acc, sm);
+    if (threadIdx.x == 0) {
+        if (job > 0)
+            for (uint32_t i = 0; i < bit + logS; i++) xyzz_dbl_cold(&acc);
+        job_out[(size_t)k * nout + blockIdx.x] = acc;
+        __threadfence();
+        ticket = atomicAdd(&done[k], 1u);
+    }
+    __syncthreads();
+    if (ticket != nout - 1) return;
+    // last block of window k: every block's result is visible
+    __threadfence();
+    if (threadIdx.x < 32) {
+        XYZZ<F> v = XYZZ<F>::inf();
+        for (uint32_t o = threadIdx.x; o < nout; o += 32) {
+            const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(&job_out[(size_t)k * nout + o]);
+            XYZZ<F> q;
+            uint32_t *d = reinterpret_cast<uint32_t *>(&q);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = p[i];
+            xyzz_add_cold(&v, &q);
+        }
+        v = warp_sum_point(v);
+        if (threadIdx.x == 0) {
+            window_sums[k] = v;
+            done[k] = 0;  // ready for the next call
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------
