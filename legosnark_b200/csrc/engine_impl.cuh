@@ -205,6 +205,48 @@ void write_point(uint64_t *out, const host::HJac<HF> &p)
 // ------------------------------------------------------------------------------
 // MSM entry points
 // ------------------------------------------------------------------------------
+// n <= SMALL_MAX_N: one kernel on device 0, bases used as uploaded (no affine ingest)
+template <class F>
+int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out)
+{
+    typedef typename HostOf<F>::type HF;
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        MsmGeom g;
+        g.c = SMALL_C;
+        g.W = SMALL_W;
+        g.B = SMALL_NBK;
+        g.NB = g.W * g.B;
+        g.L = 0;
+        D.scalars.ensure(n * sizeof(Fr));
+        D.bases_jac.ensure(n * sizeof(Jacobian<F>));
+        D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
+        D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
+        cudaStream_t st = D.stream;
+        CK(cudaMemcpyAsync(D.scalars.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(D.bases_jac.p, bases, n * sizeof(Jacobian<F>), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(D.ev[0], st));
+        CK(cudaEventRecord(D.ev[2], st));
+        LAUNCH(D, (k_msm_small<F>), g.W, SMALL_THREADS, 0, st, D.bases_jac.as<Jacobian<F>>(), D.scalars.as<Fr>(), (uint32_t)n,
+               D.window_sums.as<XYZZ<F>>());
+        CK(cudaEventRecord(D.ev[3], st));
+        CK(cudaMemcpyAsync(D.h_pinned, D.window_sums.p, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(D.ev[1], st));
+        CK(cudaStreamSynchronize(st));
+        const auto t0 = std::chrono::steady_clock::now();
+        write_point<HF>(out, finalize_windows<F>(D, g));
+        const auto t1 = std::chrono::steady_clock::now();
+        const uint32_t tot[2] = {0, 0};
+        fill_stats(D, n, g, tot, std::chrono::duration<double, std::micro>(t1 - t0).count(),
+                   (double)n * (sizeof(Fr) + sizeof(Jacobian<F>)), (double)g.W * sizeof(XYZZ<F>));
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
 template <class F>
 int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out)
 {
@@ -216,6 +258,7 @@ int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t 
         write_point<HF>(out, J::inf());
         return B200_OK;
     }
+    if (n <= SMALL_MAX_N && g_tune_c == 0) return msm_small_host<F>(bases, scalars, n, out);
     try {
         const auto ranges = split_range(n, g_devs.size());
         std::vector<J> partials(ranges.size(), J::inf());

@@ -610,6 +610,100 @@ __global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits(const XYZZ<F> *__r
 }
 
 // ------------------------------------------------------------------------------
+// small MSMs (n <= SMALL_MAX_N: CPlink's prove is one G1 MSM of 1026 points,
+// LS/gadgets/subspace.cc:78-85; sparse-matrix keygen issues thousands of 1-2 term ones,
+// LS/utils/sparsemexp.h:62-90).  At these sizes the multi-kernel pipeline is all launch and
+// dependency latency, so ONE kernel does the whole job on the bases as they came from the host
+// (Jacobian, any Z): block k owns window k; it recodes every scalar, counting-sorts the window's
+// digits in shared memory, one warp per bucket sums its points (lanes stride, then a shuffle
+// tree), and warp 0 forms sum_j (j + 1) B_j with a suffix scan.  Serial depth ~ n/512 + 13
+// point operations; the W window sums go to the host Horner like the big path's.
+// ------------------------------------------------------------------------------
+constexpr uint32_t SMALL_C = 5;                       // window bits
+constexpr uint32_t SMALL_NBK = 1u << (SMALL_C - 1);   // buckets = warps per block
+constexpr uint32_t SMALL_THREADS = 32 * SMALL_NBK;
+constexpr uint32_t SMALL_W = (255 + SMALL_C - 1) / SMALL_C;
+constexpr uint32_t SMALL_MAX_N = 4096;
+
+template <class F>
+__global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const Jacobian<F> *__restrict__ bases, const Fr *__restrict__ scalars_mont,
+                                                              uint32_t n, XYZZ<F> *__restrict__ window_sums)
+{
+    __shared__ uint16_t sh_idx[SMALL_MAX_N];  // bucket-ordered point indices, bit 15 = negate
+    __shared__ int8_t sh_dig[SMALL_MAX_N];    // signed digit of point i in this window
+    __shared__ uint32_t sh_cnt[SMALL_NBK], sh_off[SMALL_NBK + 1], sh_cur[SMALL_NBK];
+    __shared__ XYZZ<F> sh_bsum[SMALL_NBK];
+    const uint32_t k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < SMALL_NBK) sh_cnt[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += SMALL_THREADS) {
+        int d = 0;
+        if (!bases[i].z.is_zero()) {
+            const Fr s = Fr::from_mont(scalars_mont[i]);
+            for_each_digit(s, SMALL_C, SMALL_W, [&](uint32_t kk, uint32_t mag, uint32_t neg) {
+                if (kk == k) d = neg ? -(int)mag : (int)mag;
+            });
+        }
+        sh_dig[i] = (int8_t)d;
+        if (d) atomicAdd(&sh_cnt[(d < 0 ? -d : d) - 1], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t o = 0;
+        for (uint32_t j = 0; j < SMALL_NBK; j++) {
+            sh_off[j] = o;
+            sh_cur[j] = o;
+            o += sh_cnt[j];
+        }
+        sh_off[SMALL_NBK] = o;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += SMALL_THREADS) {
+        const int d = sh_dig[i];
+        if (d) {
+            const uint32_t pos = atomicAdd(&sh_cur[(d < 0 ? -d : d) - 1], 1u);
+            sh_idx[pos] = (uint16_t)(i | (d < 0 ? 0x8000u : 0u));
+        }
+    }
+    __syncthreads();
+    // warp = bucket
+    {
+        const F one = F::one();
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t e = sh_off[warp] + lane; e < sh_off[warp + 1]; e += 32) {
+            const uint32_t ix = sh_idx[e];
+            Jacobian<F> p = bases[ix & 0x7fffu];
+            if (ix & 0x8000u) p.y = F::neg(p.y);
+            if (p.z == one) {
+                const Affine<F> a{p.x, p.y};
+                xyzz_madd_cold(&acc, &a, false);
+            } else {
+                const XYZZ<F> q = XYZZ<F>::from_jacobian(p);
+                xyzz_add_cold(&acc, &q);
+            }
+        }
+        // shuffle tree only as deep as the bucket is full (tiny MSMs: 0-2 entries per bucket)
+        const uint32_t m = sh_off[warp + 1] - sh_off[warp];
+        int width = 1;
+        while (width < 32 && (uint32_t)width < m) width <<= 1;
+        acc = warp_sum_point(acc, width);
+        if (lane == 0) sh_bsum[warp] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // suffix sums P_l = sum_{m >= l} B_m, then sum_l P_l = sum_m (m + 1) B_m
+        XYZZ<F> v = lane < SMALL_NBK ? sh_bsum[lane] : XYZZ<F>::inf();
+#pragma unroll 1
+        for (uint32_t o = 1; o < SMALL_NBK; o <<= 1) {
+            const XYZZ<F> other = shfl_down_point(v, (int)o);
+            if (lane + o < SMALL_NBK) xyzz_add_cold(&v, &other);
+        }
+        v = warp_sum_point(v, (int)SMALL_NBK);
+        if (lane == 0) window_sums[k] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------
 // fixed-base tables (get_window_table / windowed_exp / batch_exp, multiexp.tcc:547-646)
 // table[o][d] = d * 2^(o w) * g, affine, (0,0) for d = 0; rows = ceil(254 / w)
 // ------------------------------------------------------------------------------
