@@ -158,6 +158,10 @@ typedef struct {
 int b200_last_stats(b200_stats_t *out);
 /* Overrides for tuning / tests: window bits c (0 = auto), chunk length L (0 = auto). */
 int b200_set_tuning(int window_bits, int chunk_len);
+/* Host-buffer MSMs (b200_msm_g1/g2) upload their inputs in `chunks` index chunks whose H2D copy
+ * overlaps the sort + accumulation of the previous chunk (0 = auto: 1 below 2^17 points, 2 below
+ * 2^19, else 4; at most 16).  1 disables the pipeline. */
+int b200_set_pipeline_chunks(int chunks);
 /* IMAD roofline microbenchmark on every SM of device 0; returns multiply-adds (lane-ops)
  * per second.  kind 0: the 32x32+64 multiply-add stream of the Montgomery product
  * (IMAD.WIDE.U32 / IMAD.WIDE.U32.X carry rows, 16 wide + 1 narrow per step; `iters` rounds

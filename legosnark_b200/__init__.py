@@ -24,7 +24,7 @@ import numpy as np
 __all__ = [
     "B200Error", "init", "init_devices", "shutdown", "device_count", "lib", "library_path",
     "multi_exp", "multi_exp_with_mixed_addition", "get_exp_window_size", "get_window_table", "batch_exp",
-    "batch_exp_with_coeff", "batch_to_special", "CommitmentKey", "sum_partials", "shard_range", "WindowTable", "last_stats", "set_tuning",
+    "batch_exp_with_coeff", "batch_to_special", "CommitmentKey", "sum_partials", "shard_range", "WindowTable", "last_stats", "set_tuning", "set_pipeline_chunks",
     "imad_peak", "test_field_op", "test_group_op",
 ]
 
@@ -281,6 +281,11 @@ def last_stats() -> dict:
 
 def set_tuning(window_bits: int = 0, chunk_len: int = 0):
     _check(lib().b200_set_tuning(int(window_bits), int(chunk_len)), "b200_set_tuning")
+
+
+def set_pipeline_chunks(chunks: int = 0):
+    """Upload chunks of a host-buffer multi_exp (0 = auto, 1 = no pipelining)."""
+    _check(lib().b200_set_pipeline_chunks(int(chunks)), "b200_set_pipeline_chunks")
 
 
 def imad_peak(kind: int = 0, iters: int = 4096):

@@ -71,16 +71,21 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+constexpr size_t MAX_CHUNKS = 16;  // upload chunks of one pipelined host-buffer MSM
+
 struct Device {
     int id = 0;
     int sms = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute (and every copy of the non-pipelined calls)
+    cudaStream_t copy_stream = nullptr;  // H2D of the next chunk while the previous one is accumulated
+    cudaEvent_t ev_ready[MAX_CHUNKS] = {};  // chunk j has landed on the device
+    cudaEvent_t ev_sync = nullptr;
     // inputs
     DevBuf scalars, bases_jac, bases_aff, flags, prefix;
     // sort
     DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, meta, order, len_hist, len_cursor;
     // accumulation / reduction
-    DevBuf partial, seg_run, seg_acc, job_out, split, done, window_sums;
+    DevBuf partial, seg_run, seg_acc, job_out, split, done, window_sums, bucket_sum;
     // batch_exp
     DevBuf out_jac, out_norm, coeff;
     void *h_pinned = nullptr;  // small pinned staging (window sums, totals)
@@ -100,7 +105,7 @@ struct Device {
     {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
-                         &entries, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &out_jac,
+                         &entries, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
                          &out_norm, &coeff};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
@@ -108,6 +113,14 @@ struct Device {
         h_pinned_cap = 0;
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        copy_stream = nullptr;
+        for (auto &e : ev_ready) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+        if (ev_sync) cudaEventDestroy(ev_sync);
+        ev_sync = nullptr;
         for (auto &e : ev) {
             if (e) cudaEventDestroy(e);
             e = nullptr;
@@ -141,7 +154,7 @@ extern std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
 extern std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
-extern int g_tune_c, g_tune_L;
+extern int g_tune_c, g_tune_L, g_tune_chunks;
 
 inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 

@@ -28,7 +28,7 @@ std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
 std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
-int g_tune_c = 0, g_tune_L = 0;
+int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0;
 
 std::vector<std::pair<size_t, size_t>> split_range(size_t n, size_t parts)
 {
@@ -88,7 +88,10 @@ int init_devices(const int *ids, int n)
             CK(cudaGetDeviceProperties(&prop, D.id));
             D.sms = prop.multiProcessorCount;
             CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
             for (auto &e : D.ev) CK(cudaEventCreate(&e));
+            for (auto &e : D.ev_ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&D.ev_sync, cudaEventDisableTiming));
         }
     } catch (const CudaError &e2) {
         g_devs.clear();
@@ -330,6 +333,13 @@ int b200_set_tuning(int window_bits, int chunk_len)
     std::lock_guard<std::mutex> lk(g_mu);
     g_tune_c = window_bits;
     g_tune_L = chunk_len;
+    return B200_OK;
+}
+
+int b200_set_pipeline_chunks(int chunks)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_tune_chunks = chunks;
     return B200_OK;
 }
 

@@ -98,48 +98,66 @@ inline void fill_stats(const Device &D, size_t n, const MsmGeom &g, const uint32
 }
 
 // ------------------------------------------------------------------------------
-// one device, one shard: enqueue the whole MSM on `st`; window sums land in D.h_pinned
+// one device, one shard.  The MSM is enqueued in three stages so that a host-buffer call can
+// pipeline its upload: plan (geometry + scratch), sort + accumulate (once, or once per chunk
+// of points followed by a fold into the dense bucket array), window reduction.
 // ------------------------------------------------------------------------------
+struct MsmPlan {
+    MsmGeom g;
+    size_t max_entries, max_tasks, nseg;
+    uint32_t ntiles, logS, M, njobs;
+};
+
+// n: points of the whole shard (decides the geometry); chunk_max: most points one sort handles
 template <class F>
-MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const uint8_t *d_flags, const Fr *d_scalars,
-                    size_t n)
+MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool dense)
 {
-    const MsmGeom g = choose_geometry(n);
-    const size_t max_entries = (size_t)g.W * n;
-    if (max_entries >= (1ull << 32)) throw CudaError{"MSM shard too large: W * n must stay below 2^32 entries"};
-    const size_t max_tasks = max_entries / g.L + g.NB;
-    const uint32_t ntiles = cdiv(g.NB, SCAN_TILE);
+    MsmPlan P;
+    const MsmGeom g = P.g = choose_geometry(n);
+    P.max_entries = (size_t)g.W * chunk_max;
+    if (P.max_entries >= (1ull << 32)) throw CudaError{"MSM shard too large: W * n must stay below 2^32 entries"};
+    P.max_tasks = P.max_entries / g.L + g.NB;
+    P.ntiles = cdiv(g.NB, SCAN_TILE);
     // window reduction geometry: segments of S = 2^logS buckets, M segments per window
-    uint32_t logS = 3;
-    while ((1u << logS) > g.B) logS--;
-    const uint32_t M = g.B >> logS;
-    uint32_t njobs = 1;
-    while ((1u << (njobs - 1)) < M) njobs++;  // job 0 + one job per bit of the segment index
-    const size_t nseg = (size_t)g.W * M;
+    P.logS = 3;
+    while ((1u << P.logS) > g.B) P.logS--;
+    P.M = g.B >> P.logS;
+    P.njobs = 1;
+    while ((1u << (P.njobs - 1)) < P.M) P.njobs++;  // job 0 + one job per bit of the segment index
+    P.nseg = (size_t)g.W * P.M;
 
     D.cnt.ensure((size_t)g.NB * 4);
     D.off.ensure((size_t)g.NB * 4);
     D.cursor.ensure((size_t)g.NB * 4);
     D.toff.ensure((size_t)g.NB * 4);
-    D.tile_sums.ensure((size_t)ntiles * sizeof(uint2));
+    D.tile_sums.ensure((size_t)P.ntiles * sizeof(uint2));
     D.totals.ensure(16);
-    D.entries.ensure(max_entries * 4);
-    D.meta.ensure(max_tasks * sizeof(uint2));
-    D.order.ensure(max_tasks * 4);
+    D.entries.ensure(P.max_entries * 4);
+    D.meta.ensure(P.max_tasks * sizeof(uint2));
+    D.order.ensure(P.max_tasks * 4);
     D.len_hist.ensure((size_t)(g.L + 1) * 4);
     D.len_cursor.ensure((size_t)(g.L + 1) * 4);
-    D.partial.ensure(max_tasks * sizeof(XYZZ<F>));
-    D.seg_run.ensure(nseg * sizeof(XYZZ<F>));
-    D.seg_acc.ensure(nseg * sizeof(XYZZ<F>));
-    D.job_out.ensure((size_t)g.W * (njobs + 1) * RED2_SPLIT * sizeof(XYZZ<F>));
-    D.split.ensure(std::min<size_t>(g.NB, max_tasks) * 4 + 4);
+    D.partial.ensure(P.max_tasks * sizeof(XYZZ<F>));
+    D.seg_run.ensure(P.nseg * sizeof(XYZZ<F>));
+    D.seg_acc.ensure(P.nseg * sizeof(XYZZ<F>));
+    D.job_out.ensure((size_t)g.W * (P.njobs + 1) * RED2_SPLIT * sizeof(XYZZ<F>));
+    D.split.ensure(std::min<size_t>(g.NB, P.max_tasks) * 4 + 4);
+    if (dense) D.bucket_sum.ensure((size_t)g.NB * sizeof(XYZZ<F>));
     if (D.done.cap < (size_t)g.W * 4) {
         D.done.ensure(1024 * 4);
         CK(cudaMemsetAsync(D.done.p, 0, D.done.cap, st));  // k_reduce_bits leaves the counters at zero
     }
     D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
     D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
+    return P;
+}
 
+// bucket sort of the digits of `n` scalars and accumulation of the bucket (task) sums into D.partial
+template <class F>
+void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const Affine<F> *d_aff, const uint8_t *d_flags,
+                             const Fr *d_scalars, size_t n)
+{
+    const MsmGeom &g = P.g;
     CK(cudaMemsetAsync(D.cnt.p, 0, (size_t)g.NB * 4, st));
     CK(cudaMemsetAsync(D.len_hist.p, 0, (size_t)(g.L + 1) * 4, st));
 
@@ -147,16 +165,15 @@ MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const ui
     uint32_t *toff = D.toff.as<uint32_t>(), *totals = D.totals.as<uint32_t>(), *entries = D.entries.as<uint32_t>();
     uint2 *tile_sums = D.tile_sums.as<uint2>(), *meta = D.meta.as<uint2>();
     uint32_t *order = D.order.as<uint32_t>(), *len_hist = D.len_hist.as<uint32_t>(), *len_cursor = D.len_cursor.as<uint32_t>();
-    XYZZ<F> *partial = D.partial.as<XYZZ<F>>(), *seg_run = D.seg_run.as<XYZZ<F>>(), *seg_acc = D.seg_acc.as<XYZZ<F>>(),
-            *job_out = D.job_out.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
+    XYZZ<F> *partial = D.partial.as<XYZZ<F>>();
 
     const uint32_t pblocks = cdiv(n, 256);
-    CK(cudaEventRecord(D.ev[0], st));
     LAUNCH(D, k_digit_count, pblocks, 256, 0, st, d_scalars, d_flags, n, g, cnt);
-    LAUNCH(D, k_scan_tile_sums, ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums);
-    LAUNCH(D, k_scan_tiles, 1, 1024, 0, st, tile_sums, ntiles, totals);
-    LAUNCH(D, k_scan_apply, ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
+    LAUNCH(D, k_scan_tile_sums, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums);
+    LAUNCH(D, k_scan_tiles, 1, 1024, 0, st, tile_sums, P.ntiles, totals);
+    LAUNCH(D, k_scan_apply, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
     LAUNCH(D, k_digit_scatter, pblocks, 256, 0, st, d_scalars, d_flags, n, g, cursor, entries);
+    const size_t max_tasks = (size_t)g.W * n / g.L + g.NB;
     const uint32_t tblocks = cdiv(max_tasks, 256);
     uint32_t *split = D.split.as<uint32_t>();
     LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist, split);
@@ -166,13 +183,94 @@ MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const ui
     LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
     CK(cudaEventRecord(D.ev[3], st));
     LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 8, 128, 0, st, cnt, toff, split, totals, g, partial);
-    LAUNCH(D, (k_reduce_segments<F>), cdiv(nseg, RED_THREADS), RED_THREADS, 0, st, cnt, toff, partial, g, logS, seg_run, seg_acc);
-    LAUNCH(D, (k_reduce_bits<F>), dim3((njobs + 1) * RED2_SPLIT, g.W), RED2_THREADS, 0, st, seg_run, seg_acc, M, logS, job_out, D.done.as<uint32_t>(),
-           wsums);
+}
+
+template <class F>
+void enqueue_fold(Device &D, cudaStream_t st, const MsmPlan &P, bool first)
+{
+    LAUNCH(D, (k_bucket_fold<F>), cdiv(P.g.NB, 128), 128, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(), D.partial.as<XYZZ<F>>(),
+           P.g.NB, first, D.bucket_sum.as<XYZZ<F>>());
+}
+
+// window reduction + D2H of the W window sums (and the entry / task totals of the last sort)
+template <class F>
+void enqueue_reduce(Device &D, cudaStream_t st, const MsmPlan &P, bool dense)
+{
+    const MsmGeom &g = P.g;
+    XYZZ<F> *seg_run = D.seg_run.as<XYZZ<F>>(), *seg_acc = D.seg_acc.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
+    LAUNCH(D, (k_reduce_segments<F>), cdiv(P.nseg, RED_THREADS), RED_THREADS, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(),
+           D.partial.as<XYZZ<F>>(), dense ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr, g, P.logS, seg_run, seg_acc);
+    LAUNCH(D, (k_reduce_bits<F>), dim3((P.njobs + 1) * RED2_SPLIT, g.W), RED2_THREADS, 0, st, seg_run, seg_acc, P.M, P.logS,
+           D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
     CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.W * sizeof(XYZZ<F>), totals, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.W * sizeof(XYZZ<F>), D.totals.p, 8, cudaMemcpyDeviceToHost, st));
+}
+
+// the whole MSM over bases and scalars that are already on the device; window sums land in D.h_pinned
+template <class F>
+MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const uint8_t *d_flags, const Fr *d_scalars,
+                    size_t n)
+{
+    const MsmPlan P = plan_msm<F>(D, st, n, n, false);
+    CK(cudaEventRecord(D.ev[0], st));
+    enqueue_sort_accumulate<F>(D, st, P, d_aff, d_flags, d_scalars, n);
+    enqueue_reduce<F>(D, st, P, false);
     CK(cudaEventRecord(D.ev[1], st));
-    return g;
+    return P.g;
+}
+
+// Host-buffer MSMs upload 128 B (G1) per point, which takes as long as the arithmetic: the
+// shard is cut into index chunks whose H2D copies (copy stream) run under the sort +
+// accumulation of the previous chunk (compute stream).
+inline size_t choose_chunks(size_t n)
+{
+    size_t s;
+    if (g_tune_chunks > 0) s = (size_t)g_tune_chunks;
+    else s = n < (1u << 17) ? 1 : n < (1u << 19) ? 2 : 4;
+    return std::max<size_t>(1, std::min<size_t>(std::min<size_t>(s, MAX_CHUNKS), n));
+}
+
+template <class F>
+MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *scalars, size_t n)
+{
+    const size_t S = choose_chunks(n);
+    D.scalars.ensure(n * sizeof(Fr));
+    D.bases_jac.ensure(n * sizeof(Jacobian<F>));
+    D.bases_aff.ensure(n * sizeof(Affine<F>));
+    D.flags.ensure(n);
+    cudaStream_t st = D.stream;
+    const auto upload = [&](cudaStream_t cs, size_t lo, size_t cnt) {
+        CK(cudaMemcpyAsync(D.scalars.as<Fr>() + lo, scalars + lo * 4, cnt * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(D.bases_jac.as<Jacobian<F>>() + lo, bases + lo * HostOf<F>::jac_limbs, cnt * sizeof(Jacobian<F>),
+                           cudaMemcpyHostToDevice, cs));
+    };
+    if (S == 1) {
+        upload(st, 0, n);
+        run_ingest<F, false>(D, st, D.bases_jac.as<Jacobian<F>>(), D.bases_aff.p, D.flags.as<uint8_t>(), n);
+        return enqueue_msm<F>(D, st, D.bases_aff.as<Affine<F>>(), D.flags.as<uint8_t>(), D.scalars.as<Fr>(), n);
+    }
+    const auto ranges = split_range(n, S);
+    size_t chunk_max = 0;
+    for (auto &r : ranges) chunk_max = std::max(chunk_max, r.second);
+    D.prefix.ensure(chunk_max * sizeof(F));
+    const MsmPlan P = plan_msm<F>(D, st, n, chunk_max, true);
+    CK(cudaEventRecord(D.ev[0], st));
+    // order the copy stream after whatever the compute stream still has in flight on these buffers
+    CK(cudaEventRecord(D.ev_sync, st));
+    CK(cudaStreamWaitEvent(D.copy_stream, D.ev_sync, 0));
+    for (size_t j = 0; j < ranges.size(); j++) {
+        const size_t lo = ranges[j].first, cnt = ranges[j].second;
+        upload(D.copy_stream, lo, cnt);
+        CK(cudaEventRecord(D.ev_ready[j], D.copy_stream));
+        CK(cudaStreamWaitEvent(st, D.ev_ready[j], 0));
+        run_ingest<F, false>(D, st, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
+        enqueue_sort_accumulate<F>(D, st, P, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, D.scalars.as<Fr>() + lo,
+                                   cnt);
+        enqueue_fold<F>(D, st, P, j == 0);
+    }
+    enqueue_reduce<F>(D, st, P, true);
+    CK(cudaEventRecord(D.ev[1], st));
+    return P.g;
 }
 
 // Horner over the window sums sitting in D.h_pinned (after the stream has been synchronised)
@@ -269,15 +367,7 @@ int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t 
             Device &D = g_devs[si];
             const size_t b = ranges[si].first, m = ranges[si].second;
             CK(cudaSetDevice(D.id));
-            D.scalars.ensure(m * sizeof(Fr));
-            D.bases_jac.ensure(m * sizeof(Jacobian<F>));
-            D.bases_aff.ensure(m * sizeof(Affine<F>));
-            D.flags.ensure(m);
-            CK(cudaMemcpyAsync(D.scalars.p, scalars + b * 4, m * sizeof(Fr), cudaMemcpyHostToDevice, D.stream));
-            CK(cudaMemcpyAsync(D.bases_jac.p, bases + b * HostOf<F>::jac_limbs, m * sizeof(Jacobian<F>), cudaMemcpyHostToDevice,
-                               D.stream));
-            run_ingest<F, false>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), D.bases_aff.p, D.flags.as<uint8_t>(), m);
-            geoms[si] = enqueue_msm<F>(D, D.stream, D.bases_aff.as<Affine<F>>(), D.flags.as<uint8_t>(), D.scalars.as<Fr>(), m);
+            geoms[si] = enqueue_msm_from_host<F>(D, bases + b * HostOf<F>::jac_limbs, scalars + b * 4, m);
             CK(cudaStreamSynchronize(D.stream));
         });
         const auto t0 = std::chrono::steady_clock::now();

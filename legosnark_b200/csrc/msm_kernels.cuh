@@ -499,6 +499,30 @@ __global__ void __launch_bounds__(128) k_bucket_combine(const uint32_t *__restri
     }
 }
 
+// pipelined MSMs (host bases arriving in chunks): after chunk j has been sorted and accumulated,
+// its bucket sums (first task slot of every non-empty bucket) are folded into the dense array
+// that lives across chunks; the first chunk initialises it.
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_fold(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
+                                                      const XYZZ<F> *__restrict__ partial, uint32_t NB, bool first,
+                                                      XYZZ<F> *__restrict__ dense)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    if (!cnt[b]) {
+        if (first) dense[b] = XYZZ<F>::inf();
+        return;
+    }
+    const XYZZ<F> q = partial[toff[b]];
+    if (first) {
+        dense[b] = q;
+    } else {
+        XYZZ<F> acc = dense[b];
+        xyzz_add_cold(&acc, &q);
+        dense[b] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------
 // window reduction: R_k = sum_{j=0..B-1} (j + 1) * bucket[k][j]
 // (the running-sum loop of multiexp.tcc:244-278, restructured for parallelism)
@@ -517,10 +541,14 @@ __global__ void __launch_bounds__(128) k_bucket_combine(const uint32_t *__restri
 constexpr int RED_THREADS = 128;
 constexpr int RED2_THREADS = 128;
 
+// `dense` != nullptr: bucket sums come from the dense per-bucket array that k_bucket_fold keeps
+// across the chunks of a pipelined MSM (empty buckets hold infinity); otherwise from the task
+// partials of the single sort.
 template <class F>
 __global__ void __launch_bounds__(RED_THREADS) k_reduce_segments(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
-                                                                  const XYZZ<F> *__restrict__ partial, MsmGeom g, uint32_t logS,
-                                                                  XYZZ<F> *__restrict__ seg_run, XYZZ<F> *__restrict__ seg_acc)
+                                                                  const XYZZ<F> *__restrict__ partial, const XYZZ<F> *__restrict__ dense,
+                                                                  MsmGeom g, uint32_t logS, XYZZ<F> *__restrict__ seg_run,
+                                                                  XYZZ<F> *__restrict__ seg_acc)
 {
     const uint32_t seg = blockIdx.x * RED_THREADS + threadIdx.x;  // global segment index over all windows
     const uint32_t nseg = g.NB >> logS;
@@ -529,7 +557,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_segments(const uint32_t 
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
     for (int t = (1 << logS) - 1; t >= 0; t--) {
         const uint32_t b = b0 + (uint32_t)t;
-        if (cnt[b]) {
+        if (dense) {
+            const XYZZ<F> q = dense[b];
+            xyzz_add_cold(&run, &q);
+        } else if (cnt[b]) {
             const XYZZ<F> q = partial[toff[b]];
             xyzz_add_cold(&run, &q);
         }

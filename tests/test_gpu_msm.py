@@ -34,6 +34,31 @@ def test_golden_cases_forced_geometry(engine, golden, grp):
         engine.set_tuning(0, 0)
 
 
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_pipelined_upload_chunks(engine, orc, golden, grp):
+    """Host-buffer MSMs cut into upload chunks (H2D of chunk j+1 under the accumulation of chunk j,
+    bucket sums folded into the dense array): every edge-case fixture and a uniform case, for
+    chunk counts that do and do not divide n."""
+    g = golden(f"msm_{grp}")
+    n = 9001 if grp == "g1" else 2050
+    P, _ = inputs.bases(orc, grp, n, seed=41, affine=False)
+    s = inputs.fr_uniform(orc, n, seed=42)
+    want = orc.msm(grp, P, s)
+    try:
+        for chunks, c, L in ((2, 0, 0), (3, 7, 4), (4, 10, 0), (7, 4, 2), (16, 12, 0)):
+            engine.set_tuning(c, L)
+            engine.set_pipeline_chunks(chunks)
+            assert (engine.multi_exp(grp, P, s) == want).all(), (grp, chunks, c, L)
+            if c == 0:
+                continue  # fixtures are small: they take the single-kernel path unless the geometry is forced
+            for name in g["names"]:
+                B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
+                assert (engine.multi_exp(grp, B, S) == R).all(), (grp, name, chunks, c, L)
+    finally:
+        engine.set_tuning(0, 0)
+        engine.set_pipeline_chunks(0)
+
+
 @pytest.mark.parametrize("grp,n", [("g1", 1 << 12), ("g1", (1 << 14) + 7), ("g2", 1 << 10)])
 def test_uniform_vs_oracle(engine, orc, grp, n):
     P, k = inputs.bases(orc, grp, n, seed=301)
