@@ -83,7 +83,7 @@ struct Device {
     // inputs
     DevBuf scalars, bases_jac, bases_aff, flags, prefix;
     // sort
-    DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, meta, order, len_hist, len_cursor;
+    DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, digits, meta, order, len_hist, len_cursor;
     // accumulation / reduction
     DevBuf partial, seg_run, seg_acc, job_out, split, done, window_sums, bucket_sum;
     // batch_exp
@@ -105,7 +105,7 @@ struct Device {
     {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
-                         &entries, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
+                         &entries, &digits, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
                          &out_norm, &coeff};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);

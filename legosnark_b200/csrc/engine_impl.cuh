@@ -119,8 +119,29 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     P.max_tasks = P.max_entries / g.L + g.NB;
     P.ntiles = cdiv(g.NB, SCAN_TILE);
     // window reduction geometry: segments of S = 2^logS buckets, M segments per window
-    P.logS = 3;
-    while ((1u << P.logS) > g.B) P.logS--;
+    // Segment length by a two-term model (ms; fitted to profiles/r02_launches_*): stage 1 runs
+    // 2 * 2^logS serial additions per thread in whole waves of resident warps (an XYZZ addition
+    // holds the multiply-add pipe of its scheduler for t_add); stage 2 costs ~6 additions per
+    // segment on a few hundred blocks.
+    {
+        const double t_add = (sizeof(F) == 32 ? 3.9e-3 : 11.5e-3);            // ms per warp-wide addition
+        const double wps = sizeof(F) == 32 ? 4.0 : 2.0;                       // resident warps per scheduler
+        const double cap = D.sms * 4.0 * wps;
+        double best = 1e300;
+        P.logS = 0;
+        for (uint32_t ls = 0; ls <= 8 && (1u << ls) <= g.B; ls++) {
+            const double nseg = (double)(g.NB >> ls), nwarps = std::ceil(nseg / 32.0);
+            const double waves = std::ceil(nwarps / cap);
+            // a lone warp cannot keep the pipe busy (dependent carry chains): ~1.6x slower per addition
+            const double share = std::max(1.6, std::min(wps, std::ceil(nwarps / (D.sms * 4.0))));
+            const double t1 = waves * (double)(2u << ls) * t_add * share;
+            const double t2 = 0.3 + 2.7e-6 * nseg * (sizeof(F) == 32 ? 1.0 : 3.0);
+            if (t1 + t2 < best) {
+                best = t1 + t2;
+                P.logS = ls;
+            }
+        }
+    }
     P.M = g.B >> P.logS;
     P.njobs = 1;
     while ((1u << (P.njobs - 1)) < P.M) P.njobs++;  // job 0 + one job per bit of the segment index
@@ -133,6 +154,7 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.tile_sums.ensure((size_t)P.ntiles * sizeof(uint2));
     D.totals.ensure(16);
     D.entries.ensure(P.max_entries * 4);
+    D.digits.ensure((size_t)g.W * ((chunk_max + 3) & ~(size_t)3) * 4);
     D.meta.ensure(P.max_tasks * sizeof(uint2));
     D.order.ensure(P.max_tasks * 4);
     D.len_hist.ensure((size_t)(g.L + 1) * 4);
@@ -168,11 +190,12 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
     XYZZ<F> *partial = D.partial.as<XYZZ<F>>();
 
     const uint32_t pblocks = cdiv(n, 256);
-    LAUNCH(D, k_digit_count, pblocks, 256, 0, st, d_scalars, d_flags, n, g, cnt);
+    const size_t dstride = (n + 3) & ~(size_t)3;
+    LAUNCH(D, k_digit_count, pblocks, 256, 0, st, d_scalars, d_flags, n, dstride, g, cnt, D.digits.as<uint32_t>());
     LAUNCH(D, k_scan_tile_sums, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums);
     LAUNCH(D, k_scan_tiles, 1, 1024, 0, st, tile_sums, P.ntiles, totals);
     LAUNCH(D, k_scan_apply, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
-    LAUNCH(D, k_digit_scatter, pblocks, 256, 0, st, d_scalars, d_flags, n, g, cursor, entries);
+    LAUNCH(D, k_digit_scatter, dim3(cdiv(n, 1024), g.W), 256, 0, st, D.digits.as<uint32_t>(), n, dstride, g, cursor, entries);
     const size_t max_tasks = (size_t)g.W * n / g.L + g.NB;
     const uint32_t tblocks = cdiv(max_tasks, 256);
     uint32_t *split = D.split.as<uint32_t>();

@@ -138,28 +138,50 @@ __device__ __forceinline__ void for_each_digit(const Fr &s, uint32_t c, uint32_t
     }
 }
 
+// Pass 1: one thread per point.  The scalar leaves Montgomery form once, its W signed digits are
+// counted into the bucket histogram and stored window-major, digits[k * stride + i] = |d| | sign << 31
+// (0 = nothing to add), so that pass 2 streams them back coalesced.
 static __global__ void __launch_bounds__(256) k_digit_count(const Fr *__restrict__ scalars_mont, const uint8_t *__restrict__ flags,
-                                                      size_t n, MsmGeom g, uint32_t *__restrict__ cnt)
+                                                      size_t n, size_t stride, MsmGeom g, uint32_t *__restrict__ cnt,
+                                                      uint32_t *__restrict__ digits)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (flags[i]) return;
+    if (flags[i]) {
+        for (uint32_t k = 0; k < g.W; k++) digits[(size_t)k * stride + i] = 0;
+        return;
+    }
     const Fr s = Fr::from_mont(scalars_mont[i]);
-    for_each_digit(s, g.c, g.W, [&](uint32_t k, uint32_t mag, uint32_t) { atomicAdd(&cnt[k * g.B + (mag - 1)], 1u); });
+    uint32_t next = 0;  // windows below `next` have been written
+    for_each_digit(s, g.c, g.W, [&](uint32_t k, uint32_t mag, uint32_t neg) {
+        for (; next < k; next++) digits[(size_t)next * stride + i] = 0;
+        digits[(size_t)k * stride + i] = mag | (neg << 31);
+        next = k + 1;
+        atomicAdd(&cnt[k * g.B + (mag - 1)], 1u);
+    });
+    for (; next < g.W; next++) digits[(size_t)next * stride + i] = 0;
 }
 
-static __global__ void __launch_bounds__(256) k_digit_scatter(const Fr *__restrict__ scalars_mont, const uint8_t *__restrict__ flags,
-                                                        size_t n, MsmGeom g, uint32_t *__restrict__ cursor,
-                                                        uint32_t *__restrict__ entries)
+// Pass 2: grid (points / 4, windows), four consecutive digits per thread (one 128-bit load;
+// every window's row of `digits` starts 16-byte aligned: row stride = n rounded up to 4).
+// Blocks are dispatched window-major, so the scattered 4-byte writes of one window (n * 4 bytes
+// of `entries`) and its cursors stay L2-resident instead of thrashing DRAM sectors across all
+// W * n entries.
+static __global__ void __launch_bounds__(256) k_digit_scatter(const uint32_t *__restrict__ digits, size_t n, size_t stride, MsmGeom g,
+                                                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flags[i]) return;
-    const Fr s = Fr::from_mont(scalars_mont[i]);
-    for_each_digit(s, g.c, g.W, [&](uint32_t k, uint32_t mag, uint32_t neg) {
-        const uint32_t pos = atomicAdd(&cursor[k * g.B + (mag - 1)], 1u);
-        entries[pos] = (uint32_t)i | (neg << 31);
-    });
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const uint32_t k = blockIdx.y;
+    if (i0 >= n) return;
+    const uint4 v = *reinterpret_cast<const uint4 *>(digits + (size_t)k * stride + i0);
+    const uint32_t d[4] = {v.x, v.y, v.z, v.w};
+    uint32_t pos[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+        if (d[t] && i0 + t < n) pos[t] = atomicAdd(&cursor[k * g.B + ((d[t] & 0x7fffffffu) - 1)], 1u);
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+        if (d[t] && i0 + t < n) entries[pos[t]] = (uint32_t)(i0 + t) | (d[t] & 0x80000000u);
 }
 
 // ------------------------------------------------------------------------------
