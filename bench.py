@@ -124,6 +124,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(group, log2n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[f"{group}_2p{log2n}"]
+        return float(e["dram_read_bytes"]) + float(e["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 def checker():
     from oracle.binding import Checker
     if Checker.available("ref"):
@@ -309,7 +318,7 @@ def main():
     roofline = {
         "bound": "imad", "kernel": f"k_accumulate<{'Fq' if group == 'g1' else 'Fq2'}>",
         "achieved": achieved, "peak": imad_wide_peak / 1e12, "unit": "T multiply-add/s (32x32+64, lane-ops)",
-        "frac": achieved / (imad_wide_peak / 1e12), "traffic": None,
+        "frac": achieved / (imad_wide_peak / 1e12), "traffic": ncu_traffic(group, args.log2n),
         "peak_source": "measured live on this GPU: b200_imad_peak(0) = the IMAD.WIDE.U32[.X] carry-row stream of the "
                        "Montgomery product on all SMs (hardware issue limit: 32 wide multiply-adds/clk/SM = "
                        f"{32 * 148 * 1.965e9 / 1e12:.2f} T/s at 1965 MHz, ncu sm__pipe_fmaheavy_cycles_active)",
