@@ -64,6 +64,13 @@ int b200_msm_g1(const uint64_t *bases /* n x 12 */, const uint64_t *scalars_mont
 int b200_msm_g2(const uint64_t *bases /* n x 24 */, const uint64_t *scalars_mont /* n x 4 */, size_t n,
                 uint64_t out[24]);
 
+/* knowledge_commitment<G2, G1> MSM: Groth16's B query (SNK/knowledge_commitment/kc_multiexp.tcc:21-89
+ * -> multi_exp<knowledge_commitment<T1,T2>>, called from r1cs_gg_ppzksnark.tcc:453-463; SNK =
+ * depends/libsnark/libsnark).  out_g2 = sum_i s_i g_i and out_g1 = sum_i s_i h_i over ONE scalar
+ * vector, which is uploaded once and stays on the devices for the second sum. */
+int b200_msm_g2g1(const uint64_t *g2_bases /* n x 24 */, const uint64_t *g1_bases /* n x 12 */,
+                  const uint64_t *scalars_mont /* n x 4 */, size_t n, uint64_t out_g2[24], uint64_t out_g1[12]);
+
 /* Host-side sum of partial results (north star: "each GPU returns a partial group element,
  * and the partials are summed on the host"; the serial sum at multiexp.tcc:433-438).  Used by
  * the engine for its own per-device partials and by one-process-per-GPU launchers (bench.py

@@ -1,0 +1,145 @@
+// groth16matrix_driver.cc — LegoGroth's matrix-product benchmark (BASELINE.json configs[3]):
+// Groth16 (libsnark r1cs_gg_ppzksnark) for U = M * N with n x n matrices, n^3 multiplication
+// gates built from inner_product_gadget exactly as LS/examples/legogrothmatrix.cc:62-123 does
+// (LS = /root/reference/src), plus the two Pedersen-style commitment MSMs over 3n^2+1 / 3n^2+2
+// bases with 32-bit scalars that the example times together with the prover (:139-146).
+// The shipped example loops n = 4..128 with the timings printed by libff's profiler and runs
+// into a missing-return; this harness takes n on the command line, times each
+// phase once and checks the proof.  Built from this one file by integration/Makefile against
+// the reference headers (groth16matrix_cpu, groth16matrix_cpuomp with -DMULTICORE) and with
+// legosnark_b200/shim ahead of them (groth16matrix_b200).
+//
+// The prover's four MSMs are multi_exp_with_mixed_addition<G1> (A, L queries), multi_exp<G1>
+// (H query) and kc_multi_exp_with_mixed_addition<G2,G1> (B query), r1cs_gg_ppzksnark.tcc:442-484;
+// the generator's are batch_exp / batch_exp_with_coeff / kc_batch_exp / batch_to_special,
+// :296-360.  In the b200 build each prover MSM is also recomputed with the reference's own
+// template (still reachable as libff::libff_cpu_* / libsnark::libsnark_cpu_*) on the same key and
+// witness and compared as group elements ("parity" in the JSON line) when n <= parity_max_n.
+//
+//   groth16matrix_{cpu,cpuomp,b200} [n = 16] [parity_max_n = 32]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+using namespace std;
+
+#include "globl.h"
+#include "util.h"
+
+#include <libff/common/default_types/ec_pp.hpp>
+#include <libsnark/common/default_types/r1cs_gg_ppzksnark_pp.hpp>
+#include <libsnark/gadgetlib1/gadgets/basic_gadgets.hpp>
+#include <libsnark/zk_proof_systems/ppzksnark/r1cs_gg_ppzksnark/r1cs_gg_ppzksnark.hpp>
+
+#include "harness.h"
+using harness::now_ms;
+using namespace libsnark;
+
+typedef default_r1cs_gg_ppzksnark_pp ppT;
+typedef libff::Fr<ppT> FieldT;
+
+static unsigned rand32b() { return (unsigned)(rand() % 0xFFFFFFFF); }  // legogrothmatrix.cc:29-32
+
+int main(int argc, char **argv)
+{
+    const int n = argc > 1 ? atoi(argv[1]) : 16;
+    const int parity_max_n = argc > 2 ? atoi(argv[2]) : 32;
+    libff::inhibit_profiling_info = true;
+    libff::inhibit_profiling_counters = true;
+    ppT::init_public_params();
+    srand(1);
+
+    // ---- circuit (legogrothmatrix.cc:62-123) ----
+    double t0 = now_ms();
+    protoboard<FieldT> pb;
+    vector<pb_variable_array<FieldT>> M_rows(n), N_cols(n);
+    vector<vector<pb_variable<FieldT>>> U(n, vector<pb_variable<FieldT>>(n));
+    vector<vector<inner_product_gadget<FieldT>>> ip(n);
+    for (int i = 0; i < n; i++) {
+        M_rows[i].allocate(pb, n, "M_row");
+        N_cols[i].allocate(pb, n, "N_col");
+    }
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) {
+            U[r][c].allocate(pb, "U_elt");
+            ip[r].push_back(inner_product_gadget<FieldT>(pb, M_rows[r], N_cols[c], U[r][c], "inner_product"));
+        }
+    pb.set_input_sizes(0);
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) ip[r][c].generate_r1cs_constraints();
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            pb.val(M_rows[i][j]) = FieldT::one() * rand32b();
+            pb.val(N_cols[i][j]) = FieldT::one() * rand32b();
+        }
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) ip[r][c].generate_r1cs_witness();
+    const bool sat = pb.is_satisfied();
+    const double circuit_ms = now_ms() - t0;
+    const size_t constraints = pb.num_constraints();
+
+    // ---- commitment bases / scalars of the example (legogrothmatrix.cc:128-131) ----
+    const size_t m1 = 3 * (size_t)n * n + 1, m2 = m1 + 1;
+    const vector<LG1> u2 = cputil::simpleBatchExp<LG1, LFr>(LG1::one(), harness::scalars<LFr>(m2, 21));
+    const vector<LG1> u1(u2.begin(), u2.begin() + m1);
+    vector<LFr> e1(m1), e2(m2);
+    for (auto &e : e1) e = LFr::one() * rand32b();
+    for (auto &e : e2) e = LFr::one() * rand32b();
+
+    // ---- generator ----
+    t0 = now_ms();
+    const r1cs_gg_ppzksnark_keypair<ppT> keypair = r1cs_gg_ppzksnark_generator<ppT>(pb.get_constraint_system());
+    const double keygen_ms = now_ms() - t0;
+
+    // ---- prover + the two commitment MSMs (prvFn, legogrothmatrix.cc:139-146) ----
+    t0 = now_ms();
+    const r1cs_gg_ppzksnark_proof<ppT> proof = r1cs_gg_ppzksnark_prover<ppT>(keypair.pk, pb.primary_input(), pb.auxiliary_input());
+    const double snark_prove_ms = now_ms() - t0;
+    t0 = now_ms();
+    const LG1 res1 = multiExpMA<LG1>(u1, e1);
+    const LG1 res2 = multiExpMA<LG1>(u2, e2);
+    const double commit_ms = now_ms() - t0;
+
+    t0 = now_ms();
+    const bool ok = r1cs_gg_ppzksnark_verifier_strong_IC<ppT>(keypair.vk, pb.primary_input(), proof);
+    const double verify_ms = now_ms() - t0;
+
+    // ---- parity of the prover's MSMs against the reference templates (b200 build only) ----
+    const char *parity = "n/a";
+#ifdef B200_SHIM_MULTIEXP_HPP_
+    if (n <= parity_max_n) {
+        r1cs_variable_assignment<FieldT> full = pb.primary_input();
+        full.insert(full.end(), pb.auxiliary_input().begin(), pb.auxiliary_input().end());
+        vector<FieldT> cw(1, FieldT::one());  // const_padded_assignment, r1cs_gg_ppzksnark.tcc:431-433
+        cw.insert(cw.end(), full.begin(), full.end());
+        const auto &pk = keypair.pk;
+        const size_t nv = cw.size();
+        const libff::G1<ppT> a_gpu = libff::multi_exp_with_mixed_addition<libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
+            pk.A_query.begin(), pk.A_query.begin() + nv, cw.begin(), cw.end(), 1);
+        const libff::G1<ppT> a_cpu = libff::libff_cpu_multi_exp_with_mixed_addition<libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
+            pk.A_query.begin(), pk.A_query.begin() + nv, cw.begin(), cw.end(), 1);
+        const auto b_gpu = kc_multi_exp_with_mixed_addition<libff::G2<ppT>, libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
+            pk.B_query, 0, nv, cw.begin(), cw.end(), 1);
+        const auto b_cpu = libsnark_cpu_kc_multi_exp_with_mixed_addition<libff::G2<ppT>, libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
+            pk.B_query, 0, nv, cw.begin(), cw.end(), 1);
+        const libff::G1<ppT> c_cpu = libff::libff_cpu_multi_exp_with_mixed_addition<LG1, LFr, libff::multi_exp_method_BDLO12>(
+            u1.begin(), u1.end(), e1.begin(), e1.end(), 1);
+        parity = (a_gpu == a_cpu && b_gpu.g == b_cpu.g && b_gpu.h == b_cpu.h && c_cpu == res1) ? "identical" : "MISMATCH";
+    } else {
+        parity = "skipped";
+    }
+#endif
+    (void)res2;
+    printf("{\"example\": \"groth16matrix\", \"impl\": \"%s\", \"n\": %d, \"constraints\": %zu, \"satisfied\": %s, "
+           "\"circuit_ms\": %.1f, \"keygen_ms\": %.1f, \"snark_prove_ms\": %.1f, \"commit_msm_ms\": %.2f, \"prove_ms\": %.1f, "
+           "\"verify_ms\": %.2f, \"verified\": %s, \"parity\": \"%s\"}\n",
+#if defined(B200_SHIM_MULTIEXP_HPP_)
+           "b200",
+#elif defined(MULTICORE)
+           "libff-cpu-omp",
+#else
+           "libff-cpu",
+#endif
+           n, constraints, sat ? "true" : "false", circuit_ms, keygen_ms, snark_prove_ms, commit_ms, snark_prove_ms + commit_ms,
+           verify_ms, ok ? "true" : "false", parity);
+    return (ok && sat && strcmp(parity, "MISMATCH") != 0) ? 0 : 1;
+}

@@ -23,7 +23,7 @@ import numpy as np
 
 __all__ = [
     "B200Error", "init", "init_devices", "shutdown", "device_count", "lib", "library_path",
-    "multi_exp", "multi_exp_with_mixed_addition", "get_exp_window_size", "get_window_table", "batch_exp",
+    "multi_exp", "multi_exp_with_mixed_addition", "kc_multi_exp", "get_exp_window_size", "get_window_table", "batch_exp",
     "batch_exp_with_coeff", "batch_to_special", "CommitmentKey", "sum_partials", "shard_range", "WindowTable", "last_stats", "set_tuning", "set_pipeline_chunks",
     "imad_peak", "test_field_op", "test_group_op",
 ]
@@ -133,6 +133,17 @@ def multi_exp(group, bases, scalars, chunks: int = 1, method: int = multi_exp_me
     out = np.zeros(L, dtype=np.uint64)
     _check(getattr(lib(), "b200_msm_" + group)(_p(bases), _p(scalars), _sz(bases.shape[0]), _p(out)), "b200_msm_" + group)
     return out
+
+
+def kc_multi_exp(g2_bases, g1_bases, scalars):
+    """knowledge_commitment<G2,G1> MSM (SNK/knowledge_commitment/kc_multiexp.tcc:21-89): the pair
+    (sum s_i g_i in G2, sum s_i h_i in G1) over one scalar vector, uploaded once."""
+    g2b, g1b, scalars = _arr(g2_bases, 24), _arr(g1_bases, 12), _arr(scalars, 4)
+    if not (g2b.shape[0] == g1b.shape[0] == scalars.shape[0]):
+        raise ValueError("bases and scalars differ in length")
+    o2, o1 = np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+    _check(lib().b200_msm_g2g1(_p(g2b), _p(g1b), _p(scalars), _sz(scalars.shape[0]), _p(o2), _p(o1)), "b200_msm_g2g1")
+    return o2, o1
 
 
 def multi_exp_with_mixed_addition(group, bases, scalars, chunks: int = 1, method: int = multi_exp_method_BDLO12):

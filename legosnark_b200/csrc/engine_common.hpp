@@ -155,6 +155,9 @@ extern std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
 extern int g_tune_c, g_tune_L, g_tune_chunks;
+// set while the second MSM of a knowledge-commitment pair runs: every device still holds the
+// scalars of its shard in D.scalars from the first one, so the host-buffer paths skip that upload
+extern bool g_scalars_resident;
 
 inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 

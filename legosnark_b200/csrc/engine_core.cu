@@ -29,6 +29,7 @@ std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0;
+bool g_scalars_resident = false;
 
 std::vector<std::pair<size_t, size_t>> split_range(size_t n, size_t parts)
 {
@@ -177,6 +178,27 @@ int b200_msm_g2(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64
 {
     std::lock_guard<std::mutex> lk(g_mu);
     return msm_host<Fq2>(bases, scalars, n, out);
+}
+
+int b200_msm_g2g1(const uint64_t *g2_bases, const uint64_t *g1_bases, const uint64_t *scalars, size_t n, uint64_t out_g2[24],
+                  uint64_t out_g1[12])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!out_g2 || !out_g1 || (n && (!g2_bases || !g1_bases || !scalars))) return fail(B200_ERR_ARG, "null argument");
+    int rc = msm_host<Fq2>(g2_bases, scalars, n, out_g2);
+    if (rc != B200_OK) return rc;
+    const b200_stats_t first = g_stats;
+    g_scalars_resident = n > 0;  // same n, same devices => same shard ranges: D.scalars is still valid
+    rc = msm_host<Fq>(g1_bases, scalars, n, out_g1);
+    g_scalars_resident = false;
+    if (rc == B200_OK) {  // stats describe the pair; geometry fields are the G1 half's
+        g_stats.kernel_launches += first.kernel_launches;
+        g_stats.h2d_bytes += first.h2d_bytes;
+        g_stats.d2h_bytes += first.d2h_bytes;
+        g_stats.host_finalize_us += first.host_finalize_us;
+        g_stats.device_ms += first.device_ms;
+    }
+    return rc;
 }
 
 int b200_sum_partials_g1(const uint64_t *pts, size_t n, uint64_t out[12]) { return sum_partials<host::HFq>(pts, n, out); }

@@ -263,7 +263,8 @@ MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *
     D.flags.ensure(n);
     cudaStream_t st = D.stream;
     const auto upload = [&](cudaStream_t cs, size_t lo, size_t cnt) {
-        CK(cudaMemcpyAsync(D.scalars.as<Fr>() + lo, scalars + lo * 4, cnt * sizeof(Fr), cudaMemcpyHostToDevice, cs));
+        if (!g_scalars_resident)
+            CK(cudaMemcpyAsync(D.scalars.as<Fr>() + lo, scalars + lo * 4, cnt * sizeof(Fr), cudaMemcpyHostToDevice, cs));
         CK(cudaMemcpyAsync(D.bases_jac.as<Jacobian<F>>() + lo, bases + lo * HostOf<F>::jac_limbs, cnt * sizeof(Jacobian<F>),
                            cudaMemcpyHostToDevice, cs));
     };
@@ -346,7 +347,7 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
         D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
         cudaStream_t st = D.stream;
-        CK(cudaMemcpyAsync(D.scalars.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        if (!g_scalars_resident) CK(cudaMemcpyAsync(D.scalars.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(D.bases_jac.p, bases, n * sizeof(Jacobian<F>), cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(D.ev[0], st));
         CK(cudaEventRecord(D.ev[2], st));
@@ -361,7 +362,7 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         const auto t1 = std::chrono::steady_clock::now();
         const uint32_t tot[2] = {0, 0};
         fill_stats(D, n, g, tot, std::chrono::duration<double, std::micro>(t1 - t0).count(),
-                   (double)n * (sizeof(Fr) + sizeof(Jacobian<F>)), (double)g.W * sizeof(XYZZ<F>));
+                   (double)n * ((g_scalars_resident ? 0 : sizeof(Fr)) + sizeof(Jacobian<F>)), (double)g.W * sizeof(XYZZ<F>));
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
@@ -398,7 +399,7 @@ int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t 
         for (size_t si = 0; si < ranges.size(); si++) {
             partials[si] = finalize_windows<F>(g_devs[si], geoms[si]);
             total = host::jac_add(total, partials[si]);
-            h2d += (double)ranges[si].second * (sizeof(Fr) + sizeof(Jacobian<F>));
+            h2d += (double)ranges[si].second * ((g_scalars_resident ? 0 : sizeof(Fr)) + sizeof(Jacobian<F>));
             d2h += (double)geoms[si].W * sizeof(XYZZ<F>) + 8;
         }
         write_point<HF>(out, total);

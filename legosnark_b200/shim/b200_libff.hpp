@@ -119,19 +119,55 @@ inline T msm(const T *bases, const FieldT *scalars, size_t n)
     return point_from_limbs<T>(out);
 }
 
+// (sum s_i g_i, sum s_i h_i) for g_i in a G2 group and h_i in a G1 group over one scalar vector:
+// the MSM behind libsnark's knowledge_commitment<T1,T2> (kc_multiexp.tcc:21-89).
+template <typename T1, typename T2, typename FieldT>
+inline void msm_pair(const T1 *g, const T2 *h, const FieldT *scalars, size_t n, T1 &out_g, T2 &out_h)
+{
+    static_assert(group_traits<T1>::group == 1 && group_traits<T2>::group == 0, "pair must be (G2, G1)");
+    static_assert(std::is_same<FieldT, typename T1::scalar_field>::value && sizeof(FieldT) == 32, "scalars must be the groups' Fr");
+    ensure_init();
+    uint64_t o2[24], o1[12];
+    check(b200_msm_g2g1(n ? limbs_of(g) : nullptr, n ? limbs_of(h) : nullptr,
+                        n ? reinterpret_cast<const uint64_t *>(scalars) : nullptr, n, o2, o1), "b200_msm_g2g1");
+    out_g = point_from_limbs<T1>(o2);
+    out_h = point_from_limbs<T2>(o1);
+}
+
+// The device table of the last base used per group is kept and reused: libsnark's Groth16
+// generator runs five batch_exps (and kc_batch_exp) over one G1 and one G2 table
+// (r1cs_gg_ppzksnark.tcc:296-360).  A table built for far fewer scalars than a later call brings
+// (its window grows with the batch size) is rebuilt.
+struct table_cache {
+    uint64_t handle = 0;
+    size_t built_for = 0;
+    uint64_t base[24] = {0};  // no destructor: the engine frees its tables at shutdown / process exit
+};
+
 template <typename T, typename FieldT>
 inline std::vector<T> fixed_base_exp(const T &base, const std::vector<FieldT> &v, const FieldT *coeff)
 {
     static_assert(std::is_same<FieldT, typename T::scalar_field>::value, "scalars must be the group's Fr");
     ensure_init();
     const size_t L = group_traits<T>::limbs, n = v.size();
+    const bool g1 = group_traits<T>::group == 0;
     std::vector<T> res(n, T::zero());
     if (n == 0) return res;
+    static table_cache cache[2];
+    table_cache &tc = cache[group_traits<T>::group];
+    if (!tc.handle || std::memcmp(tc.base, limbs_of(&base), L * 8) != 0 || n > 4 * tc.built_for) {
+        if (tc.handle) b200_window_table_destroy(tc.handle);
+        tc.handle = 0;
+        check(g1 ? b200_window_table_create_g1(limbs_of(&base), n, &tc.handle)
+                 : b200_window_table_create_g2(limbs_of(&base), n, &tc.handle), "b200_window_table_create");
+        std::memcpy(tc.base, limbs_of(&base), L * 8);
+        tc.built_for = n;
+    }
     std::vector<uint64_t> out(n * L);
     const uint64_t *s = reinterpret_cast<const uint64_t *>(v.data());
     const uint64_t *c = coeff ? reinterpret_cast<const uint64_t *>(coeff) : nullptr;
-    if (group_traits<T>::group == 0) check(b200_batch_exp_g1(limbs_of(&base), s, n, c, out.data()), "b200_batch_exp_g1");
-    else check(b200_batch_exp_g2(limbs_of(&base), s, n, c, out.data()), "b200_batch_exp_g2");
+    check(g1 ? b200_batch_exp_table_g1(tc.handle, s, n, c, out.data()) : b200_batch_exp_table_g2(tc.handle, s, n, c, out.data()),
+          "b200_batch_exp_table");
     for (size_t i = 0; i < n; i++) res[i] = point_from_limbs<T>(out.data() + i * L);
     return res;
 }

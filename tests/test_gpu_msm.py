@@ -138,3 +138,27 @@ def test_scalar_sum_identity_at_scale(engine, orc, grp, log2n):
     key.close()
     st = engine.last_stats()
     assert st["n"] == n and st["kernel_launches"] >= 10
+
+
+@pytest.mark.parametrize("n", [0, 1, 65, 1026, 6000])
+def test_knowledge_commitment_pair(engine, orc, n):
+    """knowledge_commitment<G2,G1> MSM (SNK/knowledge_commitment/kc_multiexp.tcc:21-89: the B query
+    of Groth16): both components over ONE scalar vector; sizes on both sides of the single-kernel
+    threshold, 0/1-heavy scalars as witnesses have them, and the pipelined upload."""
+    P2, _ = inputs.bases(orc, "g2", n, seed=501, affine=False)
+    P1, _ = inputs.bases(orc, "g1", n, seed=502, affine=False)
+    for s in (inputs.fr_uniform(orc, n, seed=503), inputs.fr_zero_one_heavy(orc, n)):
+        o2, o1 = engine.kc_multi_exp(P2, P1, s)
+        assert (o2 == orc.msm("g2", P2, s, chunks=orc.max_threads(), variant=1)).all()
+        assert (o1 == orc.msm("g1", P1, s, chunks=orc.max_threads(), variant=1)).all()
+    if n >= 6000:
+        s = inputs.fr_uniform(orc, n, seed=504)
+        try:
+            engine.set_pipeline_chunks(3)
+            o2, o1 = engine.kc_multi_exp(P2, P1, s)
+        finally:
+            engine.set_pipeline_chunks(0)
+        assert (o2 == orc.msm("g2", P2, s, chunks=orc.max_threads())).all()
+        assert (o1 == orc.msm("g1", P1, s, chunks=orc.max_threads())).all()
+        # the G1 half must not have re-uploaded the scalars
+        assert engine.last_stats()["h2d_bytes"] == n * (32 + 192 + 96)
