@@ -193,6 +193,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to every rank when N > 1; the reference arm is rank 0 alone
+        # with all the host threads it can use, so undo that default before libgomp reads it
+        if os.environ.get("OMP_NUM_THREADS") == "1" and (world > 1 or "TORCHELASTIC_RUN_ID" in os.environ):
+            os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
         run_reference(args, rank, world)
         return
 
