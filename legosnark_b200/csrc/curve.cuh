@@ -72,7 +72,7 @@ B200_COLD XYZZ<F> xyzz_dbl_affine(const F &x, const F &y)
     const F M = F::add(F::dbl(xx), xx);
     XYZZ<F> r;
     r.x = F::sub(F::sqr(M), F::dbl(S));
-    r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, y));
+    r.y = F::mul_sub(M, F::sub(S, r.x), W, y);
     r.zz = V;
     r.zzz = W;
     return r;  // y == 0 would give zz == 0 == infinity (no such point in the prime-order groups)
@@ -91,7 +91,7 @@ B200_HD XYZZ<F> xyzz_dbl(const XYZZ<F> &p)
     const F M = F::add(F::dbl(xx), xx);
     XYZZ<F> r;
     r.x = F::sub(F::sqr(M), F::dbl(S));
-    r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+    r.y = F::mul_sub(M, F::sub(S, r.x), W, p.y);
     r.zz = F::mul(V, p.zz);
     r.zzz = F::mul(W, p.zzz);
     return r;
@@ -123,7 +123,7 @@ B200_HD void xyzz_madd(XYZZ<F> &acc, const F &x2, const F &y2_in, bool negate)
     const F PPP = F::mul(P, PP);
     const F Q = F::mul(acc.x, PP);
     const F X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-    acc.y = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(acc.y, PPP));
+    acc.y = F::mul_sub(R, F::sub(Q, X3), acc.y, PPP);
     acc.x = X3;
     acc.zz = F::mul(acc.zz, PP);
     acc.zzz = F::mul(acc.zzz, PPP);
@@ -156,7 +156,7 @@ B200_HD void xyzz_add(XYZZ<F> &acc, const XYZZ<F> &q)
     const F PPP = F::mul(P, PP);
     const F Q = F::mul(U1, PP);
     const F X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-    acc.y = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(S1, PPP));
+    acc.y = F::mul_sub(R, F::sub(Q, X3), S1, PPP);
     acc.x = X3;
     acc.zz = F::mul(F::mul(acc.zz, q.zz), PP);
     acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);

@@ -9,7 +9,7 @@ B200_INSTANTIATE_GROUP(Fq)
 
 int test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out)
 {
-    if (op < 0 || op > 7 || (field == 2 && op > 5)) return fail(B200_ERR_ARG, "bad op");
+    if (op < 0 || op > 8 || (field == 2 && (op == 6 || op == 7))) return fail(B200_ERR_ARG, "bad op");
     switch (field) {
     case 0: return run_elementwise<Fq>(a, b, n, out, PrimeOp<Fq>{op});
     case 1: return run_elementwise<Fr>(a, b, n, out, PrimeOp<Fr>{op});

@@ -7,7 +7,8 @@
 
 namespace b200 {
 
-// op: 0 mul, 1 sqr, 2 add, 3 sub, 4 inverse, 5 neg, 6 from_mont (as_bigint), 7 to_mont
+// op: 0 mul, 1 sqr, 2 add, 3 sub, 4 inverse, 5 neg, 6 from_mont (as_bigint), 7 to_mont,
+//     8 a b - b (a + b)  (the fused two-product form mul_sub)
 template <class F>
 B200_HD F field_test_op(int op, const F &a, const F &b)
 {
@@ -18,6 +19,7 @@ B200_HD F field_test_op(int op, const F &a, const F &b)
     case 3: return F::sub(a, b);
     case 4: return F::inv(a);
     case 5: return F::neg(a);
+    case 8: return F::mul_sub(a, b, b, F::add(a, b));
     default: return a;
     }
 }

@@ -66,6 +66,9 @@ def test_prime_field_ops(emu, orc, field, mod, name):
     a[:10] = np.array([int_to_limbs(v) for v in xs[:10]])
     for op in (0, 1, 2, 3, 5):
         assert (field_op(emu, field, op, a, b) == orc.field_op(name, op, a, b)).all(), op
+    # op 8 = a b - b (a + b) through the fused two-product Montgomery pass
+    want8 = orc.field_op(name, 3, orc.field_op(name, 0, a, b), orc.field_op(name, 0, b, orc.field_op(name, 2, a, b)))
+    assert (field_op(emu, field, 8, a, b) == want8).all()
     nz = a[(a != 0).any(axis=1)][:200]
     assert (field_op(emu, field, 4, nz) == orc.field_op(name, 4, nz)).all()
     if name == "fr":
@@ -79,6 +82,8 @@ def test_fq2_ops(emu, orc):
     b = np.concatenate([ints_to_mont(edge_and_random(rng, 1000, Q)[::-1], Q), ints_to_mont(edge_and_random(rng, 1000, Q), Q)], axis=1)
     for op in (0, 1, 2, 3, 5):
         assert (field_op(emu, 2, op, a, b) == orc.field_op("fq2", op, a, b)).all(), op
+    want8 = orc.field_op("fq2", 3, orc.field_op("fq2", 0, a, b), orc.field_op("fq2", 0, b, orc.field_op("fq2", 2, a, b)))
+    assert (field_op(emu, 2, 8, a, b) == want8).all()
     nz = a[(a != 0).any(axis=1)][:100]
     assert (field_op(emu, 2, 4, nz) == orc.field_op("fq2", 4, nz)).all()
 

@@ -24,6 +24,9 @@ def test_prime_field_elementwise_2pow16(engine, orc, field, mod, name):
     a, b = _rand_mont(rng, n, mod), _rand_mont(rng, n, mod)[::-1].copy()
     for op in (0, 1, 2, 3, 5):
         assert (engine.test_field_op(field, op, a, b) == orc.field_op(name, op, a, b)).all(), op
+    # op 8 = a b - b (a + b): the fused two-product Montgomery pass (mul_sub)
+    want8 = orc.field_op(name, 3, orc.field_op(name, 0, a, b), orc.field_op(name, 0, b, orc.field_op(name, 2, a, b)))
+    assert (engine.test_field_op(field, 8, a, b) == want8).all()
     nz = a[(a != 0).any(axis=1)][:2000]
     assert (engine.test_field_op(field, 4, nz) == orc.field_op(name, 4, nz)).all()
     if name == "fr":
@@ -38,6 +41,8 @@ def test_fq2_elementwise(engine, orc):
     b = np.concatenate([_rand_mont(rng, n, Q)[::-1], _rand_mont(rng, n, Q)], axis=1)
     for op in (0, 1, 2, 3, 5):
         assert (engine.test_field_op(2, op, a, b) == orc.field_op("fq2", op, a, b)).all(), op
+    want8 = orc.field_op("fq2", 3, orc.field_op("fq2", 0, a, b), orc.field_op("fq2", 0, b, orc.field_op("fq2", 2, a, b)))
+    assert (engine.test_field_op(2, 8, a, b) == want8).all()
     nz = a[(a != 0).any(axis=1)][:500]
     assert (engine.test_field_op(2, 4, nz) == orc.field_op("fq2", 4, nz)).all()
 
