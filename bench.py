@@ -124,10 +124,10 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(group, log2n):
+def ncu_traffic(group, log2n, pre=False):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
     try:
-        e = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[f"{group}_2p{log2n}"]
+        e = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[f"{group}_2p{log2n}" + ("_pre" if pre else "")]
         return float(e["dram_read_bytes"]) + float(e["dram_write_bytes"])
     except Exception:
         return None
@@ -185,6 +185,9 @@ def main():
     ap.add_argument("--group", default="g1", choices=["g1", "g2"])
     ap.add_argument("--ref-log2n", type=int, default=17, help="sample size of the CPU reference legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-precompute", action="store_true",
+                    help="headline on the plain resident key (default: key extended by b200_key_precompute_*)")
+    ap.add_argument("--precompute-bits", type=int, default=0, help="window bits of the precomputed key (0 = engine's choice)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -273,6 +276,31 @@ def main():
     modmul_peak, _ = lb.imad_peak(2, 1 << 9)
     hbm_gbs, hbm_src = measured_peaks()
 
+    # ---- plain resident key first (secondary number), then the key is extended by its window
+    # multiples (one-off, timed) and the headline steps run on the precomputed key -------------
+    plain = None
+    if not args.no_precompute:
+        for _ in range(args.warmup):
+            step_resident()
+        barrier()
+        pl_ms, pl_acc = [], []
+        for _ in range(args.steps):
+            res_plain, ms, stp = step_resident()
+            pl_ms.append(ms)
+            pl_acc.append(stp["accumulate_ms"])
+        barrier()
+        tot_pl = float(np.sum(pl_ms))
+        if world > 1:
+            t = torch.tensor([tot_pl], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot_pl = float(t[0])
+        t0 = time.perf_counter()
+        key.precompute(args.precompute_bits)
+        pre_ms = (time.perf_counter() - t0) * 1e3
+        plain = {"value": world * n / (tot_pl / args.steps * 1e-3), "unit": UNIT, "ms_per_step": tot_pl / args.steps,
+                 "window_bits": stp["window_bits"], "windows": stp["num_windows"], "k_accumulate_ms": float(np.mean(pl_acc)),
+                 "mixed_adds": stp["num_entries"], "key_precompute_ms_one_off": pre_ms}
+
     # ---- warm-up, then exactly K timed steps of each flavour ----------------------------
     for _ in range(args.warmup):
         step_resident()
@@ -301,6 +329,8 @@ def main():
         e2e_ms.append(ms)
     barrier()
     assert (res2 == result).all(), "host-buffer path and resident path disagree"
+    if plain is not None:
+        assert (res_plain == result).all(), "precomputed key and plain key disagree"
 
     tot_res, tot_e2e = float(np.sum(res_ms)), float(np.sum(e2e_ms))
     if world > 1:
@@ -322,7 +352,7 @@ def main():
     roofline = {
         "bound": "imad", "kernel": f"k_accumulate<{'Fq' if group == 'g1' else 'Fq2'}>",
         "achieved": achieved, "peak": imad_wide_peak / 1e12, "unit": "T multiply-add/s (32x32+64, lane-ops)",
-        "frac": achieved / (imad_wide_peak / 1e12), "traffic": ncu_traffic(group, args.log2n),
+        "frac": achieved / (imad_wide_peak / 1e12), "traffic": ncu_traffic(group, args.log2n, plain is not None),
         "peak_source": "measured live on this GPU: b200_imad_peak(0) = the IMAD.WIDE.U32[.X] carry-row stream of the "
                        "Montgomery product on all SMs (hardware issue limit: 32 wide multiply-adds/clk/SM = "
                        f"{32 * 148 * 1.965e9 / 1e12:.2f} T/s at 1965 MHz, ncu sm__pipe_fmaheavy_cycles_active)",
@@ -358,6 +388,9 @@ def main():
             "config": {"workload": f"{group} MSM 2^{args.log2n} points per GPU (BASELINE.json configs[1])",
                        "points_per_gpu": n, "window_bits": stats["window_bits"], "windows": stats["num_windows"],
                        "scalars": "uniform 253-bit", "bases": "k_i*G, distinct, resident in HBM for `value`",
+                       "key": ("plain affine key" if plain is None else
+                               f"precomputed key: window multiples 2^(c k) P_i resident in HBM ({stats['num_windows']} x 64 B per base), "
+                               "all windows share one bucket set; one-off cost in plain_key.key_precompute_ms_one_off"),
                        "l2": "flushed between timed iterations (512 MiB write)", "sharding": f"index range x{world}, host sum of partials"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": stats2_bytes(st2, "h2d_bytes") * world,
@@ -366,7 +399,7 @@ def main():
             "gpu_launches": int(stats["kernel_launches"]) * args.steps,
             "launches_per_step": int(stats["kernel_launches"]),
             "host_finalize_us": float(np.mean(fin_us)),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "plain_key": plain,
         }), flush=True)
     key.close()
     lb.shutdown()

@@ -90,6 +90,18 @@ int b200_unpin_bases(uint64_t handle);
 int b200_msm_pinned_g1(uint64_t handle, size_t offset, const uint64_t *scalars_mont, size_t n, uint64_t out[12]);
 int b200_msm_pinned_g2(uint64_t handle, size_t offset, const uint64_t *scalars_mont, size_t n, uint64_t out[24]);
 
+/* Precomputed key: extends a pinned key IN PLACE by the window multiples 2^(c k) P_i,
+ * k = 1 .. ceil(255/c)-1, as affine points in HBM (W x 64 B per G1 base: 0.9 GB at 2^20 with
+ * c = 20, 56 GB at 2^26 -- the B200's 180 GB make this affordable).  Later msm_pinned calls on
+ * the key then sort the digits of all W windows into ONE set of 2^(c-1) buckets (the digit of
+ * window k selects level k of base i), which removes the per-window bucket reduction and the
+ * Horner doublings and lets c grow (fewer windows = fewer point additions).  One-off cost:
+ * (W-1) c doublings per base; amortised over the many commitments LegoSNARK makes under one
+ * key (commit.h:149-158).  window_bits 0 = chosen for the key length.  Sub-range MSMs too short
+ * to fill the buckets keep using the plain path.  Results are the same group elements. */
+int b200_key_precompute_g1(uint64_t handle, uint32_t window_bits);
+int b200_key_precompute_g2(uint64_t handle, uint32_t window_bits);
+
 /* Scalars already in device memory (cudaMalloc / torch) on the handle's first
  * device; all kernels are enqueued on `cuda_stream` (a cudaStream_t, NULL = the
  * engine's own stream) so the caller can bracket the call with its own events.
@@ -165,6 +177,9 @@ typedef struct {
 int b200_last_stats(b200_stats_t *out);
 /* Overrides for tuning / tests: window bits c (0 = auto), chunk length L (0 = auto). */
 int b200_set_tuning(int window_bits, int chunk_len);
+/* More knobs for sweeps: "reduce_log_segment" (-1 = model), "reduce_split" (0 = auto),
+ * "use_precomputed" (0: ignore a key's precomputed levels; 1: where the cost model prefers them; 2: always). */
+int b200_set_tuning_ex(const char *key, int value);
 /* Host-buffer MSMs (b200_msm_g1/g2) upload their inputs in `chunks` index chunks whose H2D copy
  * overlaps the sort + accumulation of the previous chunk (0 = auto: 1 below 2^17 points, 2 below
  * 2^19, else 4; at most 16).  1 disables the pipeline. */

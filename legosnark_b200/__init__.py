@@ -187,6 +187,13 @@ class CommitmentKey:
             _check(getattr(lib(), "b200_pin_bases_" + group)(_p(bases), _sz(self.n), ctypes.byref(h)), "b200_pin_bases_" + group)
         self.handle = h.value
 
+    def precompute(self, window_bits: int = 0):
+        """Extend the key by its window multiples 2^(c k) P_i (b200_key_precompute_*): later
+        multi_exps sort all windows into one bucket set.  One-off cost per key."""
+        _check(getattr(lib(), "b200_key_precompute_" + self.group)(ctypes.c_uint64(self.handle), ctypes.c_uint32(int(window_bits))),
+               "b200_key_precompute_" + self.group)
+        return self
+
     def multi_exp(self, scalars, offset: int = 0):
         scalars = _arr(scalars, 4)
         out = np.zeros(_LIMBS[self.group], dtype=np.uint64)
@@ -292,6 +299,11 @@ def last_stats() -> dict:
 
 def set_tuning(window_bits: int = 0, chunk_len: int = 0):
     _check(lib().b200_set_tuning(int(window_bits), int(chunk_len)), "b200_set_tuning")
+
+
+def set_tuning_ex(key: str, value: int):
+    """Sweep knobs: reduce_log_segment (-1 = model), reduce_split (0 = auto), use_precomputed (0/1)."""
+    _check(lib().b200_set_tuning_ex(key.encode(), int(value)), "b200_set_tuning_ex")
 
 
 def set_pipeline_chunks(chunks: int = 0):

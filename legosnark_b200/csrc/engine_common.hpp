@@ -133,6 +133,9 @@ struct Shard {
     size_t begin, count;
     void *d_aff = nullptr;      // Affine<F>[count]
     uint8_t *d_flags = nullptr; // count
+    // precomputed key (b200_key_precompute_*): level k = 2^(pre_c k) * P_i at d_pre[k * count + i]
+    void *d_pre = nullptr;      // Affine<F>[pre_W * count]; level 0 is a copy of d_aff
+    uint32_t pre_c = 0, pre_W = 0;
 };
 
 struct PinnedBases {
@@ -154,7 +157,7 @@ extern std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
 extern std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
-extern int g_tune_c, g_tune_L, g_tune_chunks;
+extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre;
 // set while the second MSM of a knowledge-commitment pair runs: every device still holds the
 // scalars of its shard in D.scalars from the first one, so the host-buffer paths skip that upload
 extern bool g_scalars_resident;
@@ -196,6 +199,7 @@ void for_each_shard(size_t nshards, Fn fn)
 // instantiated for Fq in engine_g1.cu and for Fq2 in engine_g2.cu
 template <class F> int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out);
 template <class F> int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *handle);
+template <class F> int key_precompute(uint64_t handle, uint32_t window_bits);
 template <class F> int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const void *d_scalars, size_t n,
                                   void *stream, uint64_t *out);
 template <class F> int table_create(const uint64_t *base, size_t expected, uint64_t *handle);

@@ -28,7 +28,7 @@ std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
 std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
-int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0;
+int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1;
 bool g_scalars_resident = false;
 
 std::vector<std::pair<size_t, size_t>> split_range(size_t n, size_t parts)
@@ -152,6 +152,7 @@ void b200_shutdown(void)
             cudaSetDevice(g_devs[s.dev].id);
             cudaFree(s.d_aff);
             cudaFree(s.d_flags);
+            cudaFree(s.d_pre);
         }
     g_pinned.clear();
     for (auto &kv : g_tables)
@@ -233,9 +234,20 @@ int b200_unpin_bases(uint64_t handle)
         cudaSetDevice(g_devs[s.dev].id);
         cudaFree(s.d_aff);
         cudaFree(s.d_flags);
+        cudaFree(s.d_pre);
     }
     g_pinned.erase(it);
     return B200_OK;
+}
+int b200_key_precompute_g1(uint64_t handle, uint32_t window_bits)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return key_precompute<Fq>(handle, window_bits);
+}
+int b200_key_precompute_g2(uint64_t handle, uint32_t window_bits)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return key_precompute<Fq2>(handle, window_bits);
 }
 int b200_msm_pinned_g1(uint64_t handle, size_t offset, const uint64_t *scalars, size_t n, uint64_t out[12])
 {
@@ -355,6 +367,18 @@ int b200_set_tuning(int window_bits, int chunk_len)
     std::lock_guard<std::mutex> lk(g_mu);
     g_tune_c = window_bits;
     g_tune_L = chunk_len;
+    return B200_OK;
+}
+
+int b200_set_tuning_ex(const char *key, int value)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!key) return fail(B200_ERR_ARG, "null key");
+    const std::string k(key);
+    if (k == "reduce_log_segment") g_tune_logS = value;       // -1 = model
+    else if (k == "reduce_split") g_tune_split = value;       // 0 = auto
+    else if (k == "use_precomputed") g_tune_pre = value;      // 0: ignore precomputed levels of a key
+    else return fail(B200_ERR_ARG, "unknown tuning key %s", key);
     return B200_OK;
 }
 

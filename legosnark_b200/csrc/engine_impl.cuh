@@ -12,24 +12,32 @@ namespace eng {
 // ------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------
-inline MsmGeom choose_geometry(size_t n)
+// cost model (ms) shared by the plain and the precomputed-key geometries: bucket sort +
+// accumulation are linear in the W * n entries; the window reduction costs 2 XYZZ additions per
+// bucket but never less than its serial depth; the last stage is pure latency.
+inline double geometry_cost(size_t n, uint32_t c, bool pre)
+{
+    const double W = std::ceil(255.0 / c), B = (double)(1u << (c - 1));
+    const double entries = W * (double)n;
+    const double acc = std::max(entries * 1.7e-7, 0.15 + entries * 0.5e-7);
+    const double red = std::max((pre ? 1.0 : W) * B * 5.4e-7, 0.16) + 0.25;
+    return acc + red;
+}
+
+// pre_c != 0: geometry of a precomputed key (window bits fixed when the key was extended)
+inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride = 0, uint32_t pre_off = 0)
 {
     MsmGeom g;
     uint32_t best_c = 4;
-    if (g_tune_c > 0) {
+    if (pre_c) {
+        best_c = pre_c;
+    } else if (g_tune_c > 0) {
         best_c = (uint32_t)std::min(std::max(g_tune_c, 2), 24);
     } else {
-        // Time model fitted to B200 measurements (profiles/, DESIGN.md "window choice"), in ms:
-        // bucket sort + accumulation are linear in the W * n entries; the window reduction costs
-        // 2 XYZZ additions per bucket but never less than its serial depth; the last stage is
-        // pure latency.
+        // fitted to B200 measurements (profiles/, DESIGN.md "window choice")
         double best = 1e300;
         for (uint32_t c = 4; c <= 22; c++) {
-            const double W = std::ceil(255.0 / c), B = (double)(1u << (c - 1));
-            const double entries = W * (double)n;
-            const double acc = std::max(entries * 1.7e-7, 0.15 + entries * 0.5e-7);
-            const double red = std::max(W * B * 5.4e-7, 0.16) + 0.25;
-            const double cost = acc + red;
+            const double cost = geometry_cost(n, c, false);
             if (cost < best) {
                 best = cost;
                 best_c = c;
@@ -39,16 +47,38 @@ inline MsmGeom choose_geometry(size_t n)
     g.c = best_c;
     g.W = (255 + g.c - 1) / g.c;
     g.B = 1u << (g.c - 1);
-    g.NB = g.W * g.B;
+    g.Wb = pre_c ? 1 : g.W;
+    g.pre_stride = pre_c ? pre_stride : 0;
+    g.pre_off = pre_c ? pre_off : 0;
+    g.NB = g.Wb * g.B;
     if (g_tune_L > 0) {
         g.L = (uint32_t)std::min(std::max(g_tune_L, 1), 1023);
     } else {
-        const double avg = (double)n / (double)g.B;
+        const double avg = (double)n * g.W / (double)g.NB;
         uint32_t L = 32;
         while (L < 2.0 * avg && L < 512) L <<= 1;
+        // k_accumulate runs one thread per task: keep several waves of tasks in flight even when
+        // few buckets hold many entries each (a precomputed key with a small window)
+        const double cap = (double)n * g.W / (148.0 * 512.0 * 6.0);
+        while (pre_c && L > 32 && L > cap) L >>= 1;
         g.L = L;
     }
     return g;
+}
+
+// window bits for extending a key of n bases (b200_key_precompute_*)
+inline uint32_t choose_precompute_window(size_t n)
+{
+    uint32_t best_c = 8;
+    double best = 1e300;
+    for (uint32_t c = 8; c <= 22; c++) {
+        const double cost = geometry_cost(n, c, true);
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
 }
 
 template <class F>
@@ -105,15 +135,15 @@ inline void fill_stats(const Device &D, size_t n, const MsmGeom &g, const uint32
 struct MsmPlan {
     MsmGeom g;
     size_t max_entries, max_tasks, nseg;
-    uint32_t ntiles, logS, M, njobs;
+    uint32_t ntiles, logS, M, njobs, split;
 };
 
 // n: points of the whole shard (decides the geometry); chunk_max: most points one sort handles
 template <class F>
-MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool dense)
+MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool dense, const MsmGeom *forced = nullptr)
 {
     MsmPlan P;
-    const MsmGeom g = P.g = choose_geometry(n);
+    const MsmGeom g = P.g = forced ? *forced : choose_geometry(n);
     P.max_entries = (size_t)g.W * chunk_max;
     if (P.max_entries >= (1ull << 32)) throw CudaError{"MSM shard too large: W * n must stay below 2^32 entries"};
     P.max_tasks = P.max_entries / g.L + g.NB;
@@ -135,17 +165,26 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
             // a lone warp cannot keep the pipe busy (dependent carry chains): ~1.6x slower per addition
             const double share = std::max(1.6, std::min(wps, std::ceil(nwarps / (D.sms * 4.0))));
             const double t1 = waves * (double)(2u << ls) * t_add * share;
-            const double t2 = 0.3 + 2.7e-6 * nseg * (sizeof(F) == 32 ? 1.0 : 3.0);
+            // one window of buckets (precomputed key): stage 2 spreads every job over `split` blocks,
+            // each thread sums nseg / (2 * split * 128) values before the block tree
+            const double t2 = g.Wb == 1 ? 0.12 + nseg / (2.0 * 16 * RED2_THREADS) * t_add * 1.6
+                                        : 0.3 + 2.7e-6 * nseg * (sizeof(F) == 32 ? 1.0 : 3.0);
             if (t1 + t2 < best) {
                 best = t1 + t2;
                 P.logS = ls;
             }
         }
     }
+    if (g_tune_logS >= 0 && (1u << g_tune_logS) <= g.B) P.logS = (uint32_t)g_tune_logS;
     P.M = g.B >> P.logS;
     P.njobs = 1;
     while ((1u << (P.njobs - 1)) < P.M) P.njobs++;  // job 0 + one job per bit of the segment index
-    P.nseg = (size_t)g.W * P.M;
+    P.nseg = (size_t)g.Wb * P.M;
+    // blocks per job of stage 2: W windows already fill the machine with 2; a lone window
+    // (precomputed key) spreads its jobs over ~2 blocks per SM
+    P.split = RED2_SPLIT;
+    if (g.Wb == 1) P.split = std::min<uint32_t>(32, std::max<uint32_t>(2, cdiv((size_t)D.sms * 2, P.njobs + 1)));
+    if (g_tune_split > 0) P.split = (uint32_t)std::min(g_tune_split, 64);
 
     D.cnt.ensure((size_t)g.NB * 4);
     D.off.ensure((size_t)g.NB * 4);
@@ -162,15 +201,15 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.partial.ensure(P.max_tasks * sizeof(XYZZ<F>));
     D.seg_run.ensure(P.nseg * sizeof(XYZZ<F>));
     D.seg_acc.ensure(P.nseg * sizeof(XYZZ<F>));
-    D.job_out.ensure((size_t)g.W * (P.njobs + 1) * RED2_SPLIT * sizeof(XYZZ<F>));
+    D.job_out.ensure((size_t)g.Wb * (P.njobs + 1) * P.split * sizeof(XYZZ<F>));
     D.split.ensure(std::min<size_t>(g.NB, P.max_tasks) * 4 + 4);
     if (dense) D.bucket_sum.ensure((size_t)g.NB * sizeof(XYZZ<F>));
-    if (D.done.cap < (size_t)g.W * 4) {
+    if (D.done.cap < (size_t)g.Wb * 4) {
         D.done.ensure(1024 * 4);
         CK(cudaMemsetAsync(D.done.p, 0, D.done.cap, st));  // k_reduce_bits leaves the counters at zero
     }
-    D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
-    D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
+    D.window_sums.ensure((size_t)g.Wb * sizeof(XYZZ<F>));
+    D.ensure_pinned((size_t)g.Wb * sizeof(XYZZ<F>) + 64);
     return P;
 }
 
@@ -223,18 +262,18 @@ void enqueue_reduce(Device &D, cudaStream_t st, const MsmPlan &P, bool dense)
     XYZZ<F> *seg_run = D.seg_run.as<XYZZ<F>>(), *seg_acc = D.seg_acc.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
     LAUNCH(D, (k_reduce_segments<F>), cdiv(P.nseg, RED_THREADS), RED_THREADS, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(),
            D.partial.as<XYZZ<F>>(), dense ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr, g, P.logS, seg_run, seg_acc);
-    LAUNCH(D, (k_reduce_bits<F>), dim3((P.njobs + 1) * RED2_SPLIT, g.W), RED2_THREADS, 0, st, seg_run, seg_acc, P.M, P.logS,
-           D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
-    CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.W * sizeof(XYZZ<F>), D.totals.p, 8, cudaMemcpyDeviceToHost, st));
+    LAUNCH(D, (k_reduce_bits<F>), dim3((P.njobs + 1) * P.split, g.Wb), RED2_THREADS, 0, st, seg_run, seg_acc, P.M, P.logS,
+           P.split, D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
+    CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)g.Wb * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.Wb * sizeof(XYZZ<F>), D.totals.p, 8, cudaMemcpyDeviceToHost, st));
 }
 
 // the whole MSM over bases and scalars that are already on the device; window sums land in D.h_pinned
 template <class F>
 MsmGeom enqueue_msm(Device &D, cudaStream_t st, const Affine<F> *d_aff, const uint8_t *d_flags, const Fr *d_scalars,
-                    size_t n)
+                    size_t n, const MsmGeom *forced = nullptr)
 {
-    const MsmPlan P = plan_msm<F>(D, st, n, n, false);
+    const MsmPlan P = plan_msm<F>(D, st, n, n, false, forced);
     CK(cudaEventRecord(D.ev[0], st));
     enqueue_sort_accumulate<F>(D, st, P, d_aff, d_flags, d_scalars, n);
     enqueue_reduce<F>(D, st, P, false);
@@ -309,7 +348,7 @@ host::HJac<typename HostOf<F>::type> finalize_windows(const Device &D, const Msm
     static_assert(sizeof(HX) == sizeof(XYZZ<F>), "host/device XYZZ images must match");
     const HX *ws = reinterpret_cast<const HX *>(D.h_pinned);
     J acc = J::inf();
-    for (int k = (int)g.W - 1; k >= 0; k--) {
+    for (int k = (int)g.Wb - 1; k >= 0; k--) {
         if (!acc.is_inf())
             for (uint32_t i = 0; i < g.c; i++) acc = host::jac_dbl(acc);
         acc = host::jac_add(acc, host::jac_from_xyzz(ws[k].x, ws[k].y, ws[k].zz, ws[k].zzz));
@@ -341,6 +380,8 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         g.W = SMALL_W;
         g.B = SMALL_NBK;
         g.NB = g.W * g.B;
+        g.Wb = g.W;
+        g.pre_stride = g.pre_off = 0;
         g.L = 0;
         D.scalars.ensure(n * sizeof(Fr));
         D.bases_jac.ensure(n * sizeof(Jacobian<F>));
@@ -400,12 +441,12 @@ int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t 
             partials[si] = finalize_windows<F>(g_devs[si], geoms[si]);
             total = host::jac_add(total, partials[si]);
             h2d += (double)ranges[si].second * ((g_scalars_resident ? 0 : sizeof(Fr)) + sizeof(Jacobian<F>));
-            d2h += (double)geoms[si].W * sizeof(XYZZ<F>) + 8;
+            d2h += (double)geoms[si].Wb * sizeof(XYZZ<F>) + 8;
         }
         write_point<HF>(out, total);
         const auto t1 = std::chrono::steady_clock::now();
         const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)g_devs[0].h_pinned +
-                                                                 (size_t)geoms[0].W * sizeof(XYZZ<F>));
+                                                                 (size_t)geoms[0].Wb * sizeof(XYZZ<F>));
         fill_stats(g_devs[0], ranges[0].second, geoms[0], tot, std::chrono::duration<double, std::micro>(t1 - t0).count(), h2d, d2h);
         return B200_OK;
     } catch (const CudaError &e) {
@@ -449,6 +490,47 @@ int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *h
         const uint64_t h = g_next_handle++;
         g_pinned[h] = std::move(pb);
         *handle = h;
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// extend a pinned key by its window multiples (include/b200_msm.h: b200_key_precompute_*)
+template <class F>
+int key_precompute(uint64_t handle, uint32_t window_bits)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    auto it = g_pinned.find(handle);
+    if (it == g_pinned.end() || it->second->group != HostOf<F>::group) return fail(B200_ERR_ARG, "unknown bases handle");
+    if (window_bits && (window_bits < 4 || window_bits > 24)) return fail(B200_ERR_ARG, "window_bits out of range (4..24)");
+    PinnedBases &pb = *it->second;
+    try {
+        for_each_shard(pb.shards.size(), [&](size_t si) {
+            Shard &S = pb.shards[si];
+            if (S.count == 0) return;
+            Device &D = g_devs[S.dev];
+            CK(cudaSetDevice(D.id));
+            const uint32_t c = window_bits ? window_bits : choose_precompute_window(S.count);
+            const uint32_t W = (255 + c - 1) / c;
+            if ((size_t)W * S.count >= (1ull << 31)) throw CudaError{"key too long to precompute: W * n must stay below 2^31 points per device"};
+            if (S.d_pre) {
+                CK(cudaFree(S.d_pre));
+                S.d_pre = nullptr;
+            }
+            CK(cudaMalloc(&S.d_pre, (size_t)W * S.count * sizeof(Affine<F>)));
+            Affine<F> *lv = reinterpret_cast<Affine<F> *>(S.d_pre);
+            CK(cudaMemcpyAsync(lv, S.d_aff, S.count * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, D.stream));
+            D.bases_jac.ensure(S.count * sizeof(Jacobian<F>));
+            for (uint32_t k = 1; k < W; k++) {
+                LAUNCH(D, (k_key_level<F>), cdiv(S.count, 128), 128, 0, D.stream, (const Affine<F> *)(lv + (size_t)(k - 1) * S.count), c,
+                       S.count, D.bases_jac.as<Jacobian<F>>());
+                run_ingest<F, false>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), lv + (size_t)k * S.count, nullptr, S.count);
+            }
+            CK(cudaStreamSynchronize(D.stream));
+            S.pre_c = c;
+            S.pre_W = W;
+        });
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
@@ -500,7 +582,19 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
                 ds = D.scalars.as<Fr>();
             }
             const Affine<F> *aff = reinterpret_cast<const Affine<F> *>(S.d_aff) + (P.lo - S.begin);
-            geoms[pi] = enqueue_msm<F>(D, st, aff, S.d_flags + (P.lo - S.begin), ds, P.cnt);
+            // precomputed levels pay when this (sub-)range fills their one big bucket set
+            bool pre = S.d_pre && g_tune_pre && g_tune_c == 0 && P.cnt > SMALL_MAX_N;
+            if (pre && g_tune_pre != 2) {  // 2 = always (tests)
+                const MsmGeom plain = choose_geometry(P.cnt);
+                pre = geometry_cost(P.cnt, S.pre_c, true) < geometry_cost(P.cnt, plain.c, false);
+            }
+            if (pre) {
+                const MsmGeom gp = choose_geometry(P.cnt, S.pre_c, (uint32_t)S.count, (uint32_t)(P.lo - S.begin));
+                geoms[pi] = enqueue_msm<F>(D, st, reinterpret_cast<const Affine<F> *>(S.d_pre), S.d_flags + (P.lo - S.begin), ds,
+                                           P.cnt, &gp);
+            } else {
+                geoms[pi] = enqueue_msm<F>(D, st, aff, S.d_flags + (P.lo - S.begin), ds, P.cnt);
+            }
             CK(cudaStreamSynchronize(st));
         });
         const auto t0 = std::chrono::steady_clock::now();
@@ -508,12 +602,12 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
         double d2h = 0;
         for (size_t pi = 0; pi < pieces.size(); pi++) {
             total = host::jac_add(total, finalize_windows<F>(g_devs[pb.shards[pieces[pi].shard].dev], geoms[pi]));
-            d2h += (double)geoms[pi].W * sizeof(XYZZ<F>) + 8;
+            d2h += (double)geoms[pi].Wb * sizeof(XYZZ<F>) + 8;
         }
         write_point<HF>(out, total);
         const auto t1 = std::chrono::steady_clock::now();
         const Device &D0 = g_devs[pb.shards[pieces[0].shard].dev];
-        const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)D0.h_pinned + (size_t)geoms[0].W * sizeof(XYZZ<F>));
+        const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)D0.h_pinned + (size_t)geoms[0].Wb * sizeof(XYZZ<F>));
         fill_stats(D0, pieces[0].cnt, geoms[0], tot, std::chrono::duration<double, std::micro>(t1 - t0).count(),
                    d_scalars ? 0.0 : (double)n * sizeof(Fr), d2h);
         return B200_OK;
@@ -751,6 +845,7 @@ int test_group_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint32
     template int msm_host<F>(const uint64_t *, const uint64_t *, size_t, uint64_t *);                                   \
     template int pin_bases<F>(const uint64_t *, const void *, size_t, uint64_t *);                                      \
     template int msm_pinned<F>(uint64_t, size_t, const uint64_t *, const void *, size_t, void *, uint64_t *);           \
+    template int key_precompute<F>(uint64_t, uint32_t);                                                                 \
     template int table_create<F>(const uint64_t *, size_t, uint64_t *);                                                 \
     template int batch_exp_table<F>(uint64_t, const uint64_t *, const void *, size_t, const uint64_t *, uint64_t *,     \
                                     void *, void *);                                                                    \

@@ -37,8 +37,17 @@ struct MsmGeom {
     uint32_t W;   // windows
     uint32_t B;   // buckets per window = 2^(c-1)
     uint32_t L;   // max entries per accumulation task
-    uint32_t NB;  // W * B
+    uint32_t NB;  // Wb * B
+    // Precomputed keys (k_key_level): the resident table also holds 2^(c k) P_i for every
+    // window k (level k at [k * pre_stride, +count)), so the digit of window k selects a point of
+    // level k and ALL windows share one set of B buckets (Wb = 1): no per-window reduction, no
+    // Horner doublings, and c can grow (fewer windows = fewer additions) without paying
+    // W * 2^(c-1) bucket sums.  Without a precomputed table Wb = W and pre_stride = 0.
+    uint32_t Wb;          // windows of buckets: W, or 1 for a precomputed key
+    uint32_t pre_stride;  // points per level of the precomputed table (0: plain key)
+    uint32_t pre_off;     // first point of this MSM inside its level
 };
+__host__ __device__ __forceinline__ uint32_t bucket_base(const MsmGeom &g, uint32_t k) { return g.pre_stride ? 0u : k * g.B; }
 
 // ------------------------------------------------------------------------------
 // Jacobian -> affine with a per-thread shared inversion.  Thread t owns points
@@ -102,6 +111,20 @@ __global__ void k_affine_flags(const Affine<F> *__restrict__ pts, uint8_t *__res
     if (i < n) flags[i] = pts[i].is_inf() ? 1 : 0;
 }
 
+// Precomputed keys: next level of the table, out[i] = 2^c * in[i] (Jacobian; k_ingest turns it
+// into the affine level).  One-off work per key: (W - 1) * c doublings per base.
+template <class F>
+__global__ void __launch_bounds__(128) k_key_level(const Affine<F> *__restrict__ in, uint32_t c, size_t n,
+                                                    Jacobian<F> *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> p = XYZZ<F>::from_affine(in[i]);
+    if (!p.is_inf())
+        for (uint32_t t = 0; t < c; t++) xyzz_dbl_cold(&p);
+    out[i] = p.to_jacobian();
+}
+
 // ------------------------------------------------------------------------------
 // signed-digit recoding
 // ------------------------------------------------------------------------------
@@ -157,7 +180,7 @@ static __global__ void __launch_bounds__(256) k_digit_count(const Fr *__restrict
         for (; next < k; next++) digits[(size_t)next * stride + i] = 0;
         digits[(size_t)k * stride + i] = mag | (neg << 31);
         next = k + 1;
-        atomicAdd(&cnt[k * g.B + (mag - 1)], 1u);
+        atomicAdd(&cnt[bucket_base(g, k) + (mag - 1)], 1u);
     });
     for (; next < g.W; next++) digits[(size_t)next * stride + i] = 0;
 }
@@ -176,12 +199,14 @@ static __global__ void __launch_bounds__(256) k_digit_scatter(const uint32_t *__
     const uint4 v = *reinterpret_cast<const uint4 *>(digits + (size_t)k * stride + i0);
     const uint32_t d[4] = {v.x, v.y, v.z, v.w};
     uint32_t pos[4];
+    const uint32_t bb = bucket_base(g, k);
+    const uint32_t pbase = g.pre_stride ? k * g.pre_stride + g.pre_off : 0u;  // level k of a precomputed key
 #pragma unroll
     for (int t = 0; t < 4; t++)
-        if (d[t] && i0 + t < n) pos[t] = atomicAdd(&cursor[k * g.B + ((d[t] & 0x7fffffffu) - 1)], 1u);
+        if (d[t] && i0 + t < n) pos[t] = atomicAdd(&cursor[bb + ((d[t] & 0x7fffffffu) - 1)], 1u);
 #pragma unroll
     for (int t = 0; t < 4; t++)
-        if (d[t] && i0 + t < n) entries[pos[t]] = (uint32_t)(i0 + t) | (d[t] & 0x80000000u);
+        if (d[t] && i0 + t < n) entries[pos[t]] = (pbase + (uint32_t)(i0 + t)) | (d[t] & 0x80000000u);
 }
 
 // ------------------------------------------------------------------------------
@@ -608,19 +633,19 @@ __device__ __forceinline__ XYZZ<F> block_sum_point(XYZZ<F> v, XYZZ<F> *sm)
 // grid ((njobs + 1) * RED2_SPLIT, W): job 0 sums twice as many points as the others and gets
 // twice the blocks; all blocks of a launch fit the machine in one wave (serial depth matters
 // here, not throughput: a point addition issued by a lone warp takes several microseconds)
-constexpr int RED2_SPLIT = 2;
+constexpr int RED2_SPLIT = 2;  // blocks per job with W windows of buckets; a precomputed key (one window) uses more
 
 template <class F>
 __global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits(const XYZZ<F> *__restrict__ seg_run, const XYZZ<F> *__restrict__ seg_acc,
-                                                               uint32_t M, uint32_t logS, XYZZ<F> *__restrict__ job_out,
+                                                               uint32_t M, uint32_t logS, uint32_t split, XYZZ<F> *__restrict__ job_out,
                                                                uint32_t *__restrict__ done, XYZZ<F> *__restrict__ window_sums)
 {
     __shared__ XYZZ<F> sm[RED2_THREADS / 32];
     __shared__ uint32_t ticket;
     const uint32_t nout = gridDim.x, k = blockIdx.y;
-    const uint32_t job = blockIdx.x < 2 * RED2_SPLIT ? 0 : blockIdx.x / RED2_SPLIT - 1;
-    const uint32_t nparts = job == 0 ? 2 * RED2_SPLIT : RED2_SPLIT;
-    const uint32_t part = job == 0 ? blockIdx.x : blockIdx.x % RED2_SPLIT;
+    const uint32_t job = blockIdx.x < 2 * split ? 0 : blockIdx.x / split - 1;
+    const uint32_t nparts = job == 0 ? 2 * split : split;
+    const uint32_t part = job == 0 ? blockIdx.x : blockIdx.x % split;
     const XYZZ<F> *src = (job == 0 ? seg_acc : seg_run) + (size_t)k * M;
     // the segments this job sums: all of them (job 0) or those with bit (job - 1) set, enumerated
     // densely so that every thread gets the same share

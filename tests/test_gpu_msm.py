@@ -107,6 +107,41 @@ def test_pinned_key_prefixes(engine, orc, grp, n):
         key.close()
 
 
+@pytest.mark.parametrize("grp,n", [("g1", 6000), ("g2", 4500)])
+def test_precomputed_key(engine, orc, golden, grp, n):
+    """b200_key_precompute_*: the key also holds 2^(c k) P_i, all windows share one bucket set.
+    Same group element as the plain key and the oracle for several window sizes, on prefixes /
+    offset sub-ranges, with zero and repeated bases, P/-P pairs and skewed scalars."""
+    P, _ = inputs.bases(orc, grp, n, seed=351, affine=False)
+    P[5] = inputs.zero_point(grp)  # a zero base
+    P[7] = P[6]                   # repeated bases -> doubling branch inside a bucket
+    P[9] = inputs.negate(orc, grp, P[8:9])[0]  # opposite bases
+    key = engine.CommitmentKey(grp, P)
+    try:
+        engine.set_tuning_ex("use_precomputed", 2)  # always, also where the cost model prefers the plain path
+        for c in (4, 7, 11, 0):
+            key.precompute(c)
+            for m, off in ((n, 0), (n - 1, 1), (4100, 333)):
+                for s in (inputs.fr_uniform(orc, m, seed=352 + m), inputs.fr_zero_one_heavy(orc, m)):
+                    s[3:12] = s[3]  # equal scalars on the special bases
+                    want = orc.msm(grp, P[off:off + m], s, chunks=orc.max_threads())
+                    got = key.multi_exp(s, offset=off)
+                    assert (got == want).all(), (grp, c, m, off)
+            if c:
+                st = engine.last_stats()
+                assert st["window_bits"] == c, "precomputed path was not taken"
+        # short sub-ranges fall back to the plain / single-kernel paths
+        s = inputs.fr_uniform(orc, 100, seed=360)
+        assert (key.multi_exp(s, offset=37) == orc.msm(grp, P[37:137], s)).all()
+        # switching the levels off gives the plain path on the same key
+        engine.set_tuning_ex("use_precomputed", 0)
+        s = inputs.fr_uniform(orc, n, seed=361)
+        assert (key.multi_exp(s) == orc.msm(grp, P, s, chunks=orc.max_threads())).all()
+    finally:
+        engine.set_tuning_ex("use_precomputed", 1)
+        key.close()
+
+
 def _scalar_sum_expected(orc, grp, k, s):
     """(sum s_i k_i mod r) * G, with the big-integer sum vectorised over 64-bit limbs."""
     rinv = pow(MONT_R, -1, R_ORDER)
@@ -135,9 +170,13 @@ def test_scalar_sum_identity_at_scale(engine, orc, grp, log2n):
     assert (engine.multi_exp(grp, P, s) == want).all()
     key = engine.CommitmentKey(grp, P)
     assert (key.multi_exp(s) == want).all()
-    key.close()
     st = engine.last_stats()
     assert st["n"] == n and st["kernel_launches"] >= 10
+    key.precompute()  # window multiples in HBM: one bucket set for all windows
+    assert (key.multi_exp(s) == want).all()
+    st2 = engine.last_stats()
+    assert st2["num_entries"] < st["num_entries"] or log2n < 18, "precomputed key did not cut the additions"
+    key.close()
 
 
 @pytest.mark.parametrize("n", [0, 1, 65, 1026, 6000])
