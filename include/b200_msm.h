@@ -150,6 +150,36 @@ int b200_pin_affine_dev_g2(const void *d_affine, size_t n, uint64_t *handle);
 int b200_batch_to_affine_g1(uint64_t *pts, size_t n);
 int b200_batch_to_affine_g2(uint64_t *pts, size_t n);
 
+/* ---- Fr vector work on either side of the MSMs -----------
+ * All vectors hold Montgomery-form Fr elements, 4 limbs each, as the reference's
+ * std::vector<Fr> does.  LS = src/, FQFFT = depends/libsnark/depends/libfqfft/libfqfft/.
+ *
+ * Witness folding of CPPoly::prove (LS/gadgets/poly.h:45-67): v has 2^d values, r has d.
+ * Level i pairs (2p, 2p+1): w_coeffs[start_i + p] = -t[2p] + t[2p+1] and
+ * t[p] <- -t[2p] (r_i - 1) + t[2p+1] r_i, start_i = 2^d - 2^(d-i).  w_coeffs gets the
+ * reference's 2^d-entry vector (last entry zero); eval gets the last t[0], which is
+ * MultiVPolyT::evalMLE(v, r).  Either output may be NULL. */
+int b200_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs /* 2^d x 4 */, uint64_t eval[4]);
+/* MultiVPolyT::evalMLE (LS/prototools/polytools.h:207-234): sum_p v[p] prod_i (bit i of p ? r_i : 1 - r_i). */
+int b200_fr_eval_mle(const uint64_t *v /* 2^d x 4 */, const uint64_t *r /* d x 4 */, size_t d, uint64_t out[4]);
+/* DPMle::pushRandomness (LS/prototools/mle.h:199-210): out[p] = table[p] (1 - r) + table[p + half] r. */
+int b200_fr_mle_bind(const uint64_t *table /* 2 half x 4 */, size_t half, const uint64_t r[4], uint64_t *out /* half x 4 */);
+/* CPPoly::prove (poly.h:45-91) against a resident G1 key (b200_pin_bases_g1, single device):
+ * folding on the device, then witness[i] = multiExpMA(g1s, w_i) over the first 2^(d-i-1)
+ * bases with the scalars never leaving the device.  witness: d normalised points; the
+ * reference's witnessa[i] (i >= 1) repeats the same MSM over the same bases (poly.h:84-86) and
+ * equals witness[i].  eval (may be NULL) = evalMLE(v, r). */
+int b200_cppoly_prove_g1(uint64_t key_handle, const uint64_t *v, const uint64_t *r, size_t d, uint64_t *witness /* d x 12 */,
+                         uint64_t eval[4]);
+/* libfqfft basic_radix2_domain<Fr> (FQFFT/evaluation_domain/domains/basic_radix2_domain.tcc,
+ * _aux.tcc:42-75) on m = 2^log_n values in place.  mode 0: FFT, 1: iFFT (times m^-1),
+ * 2: cosetFFT(a, g), 3: icosetFFT(a, g), 4: _basic_radix2_FFT(a, omega^-1), the unscaled inverse the
+ * extended / step radix-2 domains call directly.  omega = get_root_of_unity(m) (field_utils.tcc:38-51,
+ * Fr::s = 28).  Twiddle and coset tables are built on the device and cached per size. */
+int b200_fr_fft(uint64_t *a, size_t log_n, int mode, const uint64_t *coset_g /* modes 2, 3 */);
+/* same, on a device-resident vector, enqueued on cuda_stream (bench.py / callers that chain transforms) */
+int b200_fr_fft_dev(void *d_a, size_t log_n, int mode, const uint64_t *coset_g, void *cuda_stream);
+
 /* ---- parity hooks: element-wise kernels over the device arithmetic ------------
  * field: 0 Fq, 1 Fr, 2 Fq2.  op: 0 mul, 1 sqr, 2 add, 3 sub, 4 inverse, 5 neg,
  * 6 as_bigint (Fq/Fr), 7 from bigint (Fq/Fr).  b may be NULL for unary ops. */

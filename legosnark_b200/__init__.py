@@ -290,6 +290,71 @@ def batch_to_special(group, vec):
     return vec
 
 
+# ---- Fr vector work next to the MSMs ------------------------
+def fold_witness(v, r):
+    """CPPoly::prove's folding (LS/gadgets/poly.h:45-67): (w_coeffs (2^d, 4), last tmp_v[0])."""
+    v, r = _arr(v, 4), _arr(r, 4)
+    d = r.shape[0]
+    if v.shape[0] != 1 << d:
+        raise ValueError("v must hold 2^d values")
+    w = np.zeros((1 << d, 4), dtype=np.uint64)
+    ev = np.zeros(4, dtype=np.uint64)
+    _check(lib().b200_fr_fold_witness(_p(v), _p(r), _sz(d), _p(w), _p(ev)), "b200_fr_fold_witness")
+    return w, ev
+
+
+def evalMLE(v, r):
+    """MultiVPolyT::evalMLE (LS/prototools/polytools.h:207-234)."""
+    v, r = _arr(v, 4), _arr(r, 4)
+    d = r.shape[0]
+    if v.shape[0] != 1 << d:
+        raise ValueError("assert(N == 1 << d)")  # polytools.h:211
+    out = np.zeros(4, dtype=np.uint64)
+    _check(lib().b200_fr_eval_mle(_p(v), _p(r), _sz(d), _p(out)), "b200_fr_eval_mle")
+    return out
+
+
+def mle_push_randomness(table, r):
+    """DPMle::pushRandomness (LS/prototools/mle.h:199-210) on a table of 2 * half values."""
+    table, r = _arr(table, 4), _arr(r, 4)
+    half = table.shape[0] // 2
+    out = np.zeros((half, 4), dtype=np.uint64)
+    _check(lib().b200_fr_mle_bind(_p(table), _sz(half), _p(r), _p(out)), "b200_fr_mle_bind")
+    return out
+
+
+def cppoly_prove(key: "CommitmentKey", v, r):
+    """CPPoly::prove (LS/gadgets/poly.h:45-91) against a resident G1 key: (witness (d, 12), evalMLE(v, r))."""
+    v, r = _arr(v, 4), _arr(r, 4)
+    d = r.shape[0]
+    if v.shape[0] != 1 << d:
+        raise ValueError("v must hold 2^d values")
+    wit = np.zeros((d, 12), dtype=np.uint64)
+    ev = np.zeros(4, dtype=np.uint64)
+    _check(lib().b200_cppoly_prove_g1(ctypes.c_uint64(key.handle), _p(v), _p(r), _sz(d), _p(wit), _p(ev)), "b200_cppoly_prove_g1")
+    return wit, ev
+
+
+FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
+
+
+def fr_fft(a, mode: int = FFT, g=None):
+    """libfqfft basic_radix2_domain<Fr>::FFT / iFFT / cosetFFT / icosetFFT on 2^k values; returns the transform."""
+    a = _arr(a, 4).copy()
+    n = a.shape[0]
+    log_n = n.bit_length() - 1
+    if n != 1 << log_n:
+        raise ValueError("basic_radix2: expected a power-of-two size")
+    g = None if g is None else _arr(g, 4)
+    _check(lib().b200_fr_fft(_p(a), _sz(log_n), int(mode), None if g is None else _p(g)), "b200_fr_fft")
+    return a
+
+
+def fr_fft_device(d_ptr: int, log_n: int, mode: int = FFT, g=None, stream: int = 0):
+    g = None if g is None else _arr(g, 4)
+    _check(lib().b200_fr_fft_dev(_vp(d_ptr), _sz(log_n), int(mode), None if g is None else _p(g), _vp(stream)), "b200_fr_fft_dev")
+
+
 # ---- introspection ---------------------------------------------------------------------
 def last_stats() -> dict:
     s = Stats()

@@ -88,6 +88,8 @@ struct Device {
     DevBuf partial, seg_run, seg_acc, job_out, split, done, window_sums, bucket_sum;
     // batch_exp
     DevBuf out_jac, out_norm, coeff;
+    // Fr vector kernels (engine_fr.cu): ping-pong value buffers, challenge point, witness coefficients
+    DevBuf fr_a, fr_b, fr_r, fr_w;
     void *h_pinned = nullptr;  // small pinned staging (window sums, totals)
     size_t h_pinned_cap = 0;
     uint32_t launches = 0;
@@ -106,7 +108,7 @@ struct Device {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
                          &entries, &digits, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
-                         &out_norm, &coeff};
+                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -209,6 +211,16 @@ template <class F> int batch_exp_once(const uint64_t *base, const uint64_t *scal
 template <class F> int batch_to_affine(uint64_t *pts, size_t n);
 template <class F> int test_group_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint32_t k, uint64_t *out);
 int test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);  // engine_g1.cu
+
+// Fr vector work (engine_fr.cu).  fr_fold_device: v (2^d values) and r (d values) are uploaded to
+// D.fr_a / D.fr_r, folded on D.stream; witness coefficients (if wanted) land in D.fr_w in the
+// reference's w_coeffs layout, the final value in D.fr_a[0] or D.fr_b[0] (returned pointer).
+const void *fr_fold_device(Device &D, const uint64_t *v, const uint64_t *r, size_t d, bool want_w);
+int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval);
+int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
+int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, void *stream);
+void fr_release();
+int cppoly_prove_g1(uint64_t key, const uint64_t *v, const uint64_t *r, size_t d, uint64_t *witness, uint64_t *eval);  // engine_g1.cu
 
 }  // namespace eng
 }  // namespace b200

@@ -161,6 +161,7 @@ void b200_shutdown(void)
             cudaFree(kv.second->d_table[di]);
         }
     g_tables.clear();
+    fr_release();
     for (auto &d : g_devs) d.release();
     g_devs.clear();
     g_init = false;
@@ -328,6 +329,40 @@ int b200_batch_exp_table_dev_g2(uint64_t handle, const void *d_scalars, size_t n
     std::lock_guard<std::mutex> lk(g_mu);
     if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
     return batch_exp_table<Fq2>(handle, nullptr, d_scalars, n, nullptr, nullptr, d_out, stream);
+}
+
+int b200_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t eval[4])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_fold_witness(v, r, d, w_coeffs, eval);
+}
+int b200_fr_eval_mle(const uint64_t *v, const uint64_t *r, size_t d, uint64_t out[4])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!out) return fail(B200_ERR_ARG, "null argument");
+    return fr_fold_witness(v, r, d, nullptr, out);
+}
+int b200_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t r[4], uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_mle_bind(table, half, r, out);
+}
+int b200_cppoly_prove_g1(uint64_t key, const uint64_t *v, const uint64_t *r, size_t d, uint64_t *witness, uint64_t eval[4])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return cppoly_prove_g1(key, v, r, d, witness, eval);
+}
+int b200_fr_fft(uint64_t *a, size_t log_n, int mode, const uint64_t *coset_g)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!a) return fail(B200_ERR_ARG, "null argument");
+    return fr_fft(a, nullptr, log_n, mode, coset_g, nullptr);
+}
+int b200_fr_fft_dev(void *d_a, size_t log_n, int mode, const uint64_t *coset_g, void *cuda_stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!d_a) return fail(B200_ERR_ARG, "null argument");
+    return fr_fft(nullptr, d_a, log_n, mode, coset_g, cuda_stream);
 }
 
 int b200_batch_to_affine_g1(uint64_t *pts, size_t n)

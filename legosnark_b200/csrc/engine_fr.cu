@@ -1,0 +1,235 @@
+// engine_fr.cu — host side of the Fr vector kernels (fr_kernels.cuh): multilinear folding
+// (CPPoly::prove / evalMLE / DPMle) and libfqfft's basic radix-2 domain.
+#include "engine_common.hpp"
+#include "fr_kernels.cuh"
+
+namespace b200 {
+namespace eng {
+
+// ------------------------------------------------------------------------------
+// folding
+// ------------------------------------------------------------------------------
+const void *fr_fold_device(Device &D, const uint64_t *v, const uint64_t *r, size_t d, bool want_w)
+{
+    const size_t N = (size_t)1 << d;
+    cudaStream_t st = D.stream;
+    D.fr_a.ensure(N * sizeof(Fr));
+    D.fr_b.ensure(std::max<size_t>(N / 2, 1) * sizeof(Fr));
+    D.fr_r.ensure(std::max<size_t>(d, 1) * sizeof(Fr));
+    if (want_w) {
+        D.fr_w.ensure(N * sizeof(Fr));
+        // w_coeffs is a zero-initialised vector of 2^d entries of which 2^d - 1 are written (poly.h:52)
+        CK(cudaMemsetAsync((char *)D.fr_w.p + (N - 1) * sizeof(Fr), 0, sizeof(Fr), st));
+    }
+    CK(cudaMemcpyAsync(D.fr_a.p, v, N * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (d) CK(cudaMemcpyAsync(D.fr_r.p, r, d * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    Fr *cur = D.fr_a.as<Fr>(), *nxt = D.fr_b.as<Fr>();
+    for (uint32_t i0 = 0; i0 < d;) {
+        const uint32_t nl = std::min<uint32_t>(FOLD_LEVELS, (uint32_t)d - i0);
+        const size_t pairs = (size_t)1 << (d - i0 - 1);
+        LAUNCH(D, k_fr_fold, cdiv(pairs, FOLD_THREADS), FOLD_THREADS, 0, st, (const Fr *)cur, D.fr_r.as<Fr>(), (uint32_t)d, i0, nl, nxt,
+               want_w ? D.fr_w.as<Fr>() : (Fr *)nullptr);
+        std::swap(cur, nxt);
+        i0 += nl;
+    }
+    return cur;
+}
+
+int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!v || (d && !r) || (!w_coeffs && !eval)) return fail(B200_ERR_ARG, "null argument");
+    if (d > 30) return fail(B200_ERR_ARG, "d out of range");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        const size_t N = (size_t)1 << d;
+        const void *fin = fr_fold_device(D, v, r, d, w_coeffs != nullptr);
+        if (w_coeffs) CK(cudaMemcpyAsync(w_coeffs, D.fr_w.p, N * sizeof(Fr), cudaMemcpyDeviceToHost, D.stream));
+        if (eval) CK(cudaMemcpyAsync(eval, fin, sizeof(Fr), cudaMemcpyDeviceToHost, D.stream));
+        CK(cudaStreamSynchronize(D.stream));
+        g_stats = b200_stats_t{};
+        g_stats.n = N;
+        g_stats.kernel_launches = D.launches;
+        g_stats.h2d_bytes = (double)(N + d) * sizeof(Fr);
+        g_stats.d2h_bytes = (double)((w_coeffs ? N : 0) + (eval ? 1 : 0)) * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
+    if (half == 0) return B200_OK;
+    if (!table || !r || !out) return fail(B200_ERR_ARG, "null argument");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        D.fr_a.ensure(2 * half * sizeof(Fr));
+        D.fr_b.ensure(half * sizeof(Fr));
+        D.fr_r.ensure(sizeof(Fr));
+        CK(cudaMemcpyAsync(D.fr_a.p, table, 2 * half * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(D.fr_r.p, r, sizeof(Fr), cudaMemcpyHostToDevice, st));
+        LAUNCH(D, k_fr_bind_hi, cdiv(half, 256), 256, 0, st, D.fr_a.as<Fr>(), half, D.fr_r.as<Fr>(), D.fr_b.as<Fr>());
+        CK(cudaMemcpyAsync(out, D.fr_b.p, half * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = half;
+        g_stats.kernel_launches = D.launches;
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// ------------------------------------------------------------------------------
+// radix-2 domains: twiddle tables cached per (device, log n); coset tables per last shift g
+// ------------------------------------------------------------------------------
+struct FrDomain {
+    DevBuf consts;              // omega, omega^-1, n^-1, g, g^-1
+    DevBuf tw_fwd, tw_inv;      // omega^i, omega^-i, i < n/2
+    DevBuf coset_pre;           // g^i, i < n
+    DevBuf coset_post;          // n^-1 g^-i
+    DevBuf g_dev;
+    bool has_g = false;
+    uint64_t g[4] = {0, 0, 0, 0};
+};
+static std::vector<std::map<uint32_t, std::unique_ptr<FrDomain>>> g_domains;
+
+void fr_release()
+{
+    for (size_t di = 0; di < g_domains.size(); di++) {
+        if (di < g_devs.size()) cudaSetDevice(g_devs[di].id);
+        for (auto &kv : g_domains[di]) {
+            FrDomain &dm = *kv.second;
+            DevBuf *all[] = {&dm.consts, &dm.tw_fwd, &dm.tw_inv, &dm.coset_pre, &dm.coset_post, &dm.g_dev};
+            for (DevBuf *b : all) b->release();
+        }
+    }
+    g_domains.clear();
+}
+
+static FrDomain &domain_for(Device &D, size_t dev_index, uint32_t logn, const uint64_t *g, cudaStream_t st)
+{
+    if (g_domains.size() < g_devs.size()) g_domains.resize(g_devs.size());
+    auto &slot = g_domains[dev_index][logn];
+    const size_t n = (size_t)1 << logn;
+    const bool fresh = !slot;
+    if (fresh) slot = std::make_unique<FrDomain>();
+    FrDomain &dm = *slot;
+    const bool new_g = g && (!dm.has_g || memcmp(dm.g, g, 32) != 0);
+    if (fresh || new_g) {
+        dm.consts.ensure(5 * sizeof(Fr));
+        dm.g_dev.ensure(sizeof(Fr));
+        const Fr *gd = nullptr;
+        if (g) {
+            // the table kernels run on `st`; a pageable source is copied before the call returns
+            CK(cudaMemcpyAsync(dm.g_dev.p, g, sizeof(Fr), cudaMemcpyHostToDevice, st));
+            gd = dm.g_dev.as<Fr>();
+        } else if (dm.has_g) {
+            gd = dm.g_dev.as<Fr>();  // keep the cached shift when a plain transform creates nothing new
+        }
+        LAUNCH(D, k_fr_domain_consts, 1, 32, 0, st, logn, gd, dm.consts.as<Fr>());
+    }
+    const Fr *c = dm.consts.as<Fr>();
+    if (fresh) {
+        const size_t half = std::max<size_t>(n / 2, 1);
+        dm.tw_fwd.ensure(half * sizeof(Fr));
+        dm.tw_inv.ensure(half * sizeof(Fr));
+        LAUNCH(D, k_fr_pow_table, cdiv(cdiv(half, 16), 128), 128, 0, st, c + 0, (const Fr *)nullptr, half, dm.tw_fwd.as<Fr>());
+        LAUNCH(D, k_fr_pow_table, cdiv(cdiv(half, 16), 128), 128, 0, st, c + 1, (const Fr *)nullptr, half, dm.tw_inv.as<Fr>());
+    }
+    if (new_g) {
+        dm.coset_pre.ensure(n * sizeof(Fr));
+        dm.coset_post.ensure(n * sizeof(Fr));
+        LAUNCH(D, k_fr_pow_table, cdiv(cdiv(n, 16), 128), 128, 0, st, c + 3, (const Fr *)nullptr, n, dm.coset_pre.as<Fr>());
+        LAUNCH(D, k_fr_pow_table, cdiv(cdiv(n, 16), 128), 128, 0, st, c + 4, c + 2, n, dm.coset_post.as<Fr>());
+        memcpy(dm.g, g, 32);
+        dm.has_g = true;
+    }
+    return dm;
+}
+
+// mode 0 FFT, 1 iFFT, 2 cosetFFT(g), 3 icosetFFT(g)  (basic_radix2_domain.tcc); 4: the unscaled inverse
+// transform _basic_radix2_FFT(a, omega^-1) that iFFT and the extended / step domains build on.
+// a: host vector transformed in place, or d_a: device vector transformed in place on `stream`.
+int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, void *stream)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if ((!a && !d_a) || mode < 0 || mode > 4) return fail(B200_ERR_ARG, "bad argument");
+    if (log_n < 1 || log_n > FR_TWO_ADICITY) return fail(B200_ERR_ARG, "basic_radix2: expected 1 <= log2(m) <= Fr::s = 28");
+    if ((mode == 2 || mode == 3) && !g) return fail(B200_ERR_ARG, "coset transforms need the shift g");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = (d_a && stream) ? (cudaStream_t)stream : D.stream;
+        const uint32_t logn = (uint32_t)log_n;
+        const size_t n = (size_t)1 << logn;
+        FrDomain &dm = domain_for(D, 0, logn, (mode == 2 || mode == 3) ? g : nullptr, st);
+        Fr *data;
+        D.fr_b.ensure(n * sizeof(Fr));
+        if (d_a) {
+            data = reinterpret_cast<Fr *>(d_a);
+        } else {
+            D.fr_a.ensure(n * sizeof(Fr));
+            CK(cudaMemcpyAsync(D.fr_a.p, a, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            data = D.fr_a.as<Fr>();
+        }
+        Fr *work = D.fr_b.as<Fr>();
+        const bool inverse = mode == 1 || mode == 3 || mode == 4;
+        const Fr *tw = inverse ? dm.tw_inv.as<Fr>() : dm.tw_fwd.as<Fr>();
+        const Fr *pre = mode == 2 ? dm.coset_pre.as<Fr>() : nullptr;
+        const Fr *post = mode == 3 ? dm.coset_post.as<Fr>() : nullptr;
+        const Fr *post_scalar = mode == 1 ? dm.consts.as<Fr>() + 2 : nullptr;
+        // pass plan: the first pass does up to 10 stages on contiguous tiles; the remaining stages are
+        // split evenly over passes of at most 8 stages, each block taking 2^(10-k) low-index neighbours
+        std::vector<FftPass> plan;
+        const uint32_t k1 = std::min<uint32_t>(FFT_TILE_LOG, logn);
+        plan.push_back(FftPass{logn, 0, k1, 0});
+        uint32_t rem = logn - k1;
+        if (rem) {
+            const uint32_t np = (rem + 7) / 8;
+            uint32_t s0 = k1;
+            for (uint32_t p = 0; p < np; p++) {
+                const uint32_t k = (rem + (np - p) - 1) / (np - p);
+                plan.push_back(FftPass{logn, s0, k, (uint32_t)FFT_TILE_LOG - k});
+                s0 += k;
+                rem -= k;
+            }
+        }
+        // data -> work (bit reversal cannot run in place), middle passes in place on work, the last
+        // pass writes back to data; a one-pass transform is copied back
+        for (size_t pi = 0; pi < plan.size(); pi++) {
+            const FftPass &P = plan[pi];
+            const bool last = pi + 1 == plan.size();
+            const Fr *src = pi == 0 ? data : work;
+            Fr *dst = (last && pi > 0) ? data : work;
+            const uint32_t E = 1u << (P.k + P.t);
+            LAUNCH(D, k_fr_fft_pass, (uint32_t)(n / E), FFT_THREADS, (size_t)8 * E * 4, st, src, dst, P, tw, pi == 0 ? pre : (const Fr *)nullptr,
+                   last ? post : (const Fr *)nullptr, last ? post_scalar : (const Fr *)nullptr);
+        }
+        if (plan.size() == 1) CK(cudaMemcpyAsync(data, work, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        if (!d_a) {
+            CK(cudaMemcpyAsync(a, data, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        g_stats = b200_stats_t{};
+        g_stats.n = n;
+        g_stats.kernel_launches = D.launches;
+        g_stats.num_windows = (uint32_t)plan.size();
+        g_stats.h2d_bytes = d_a ? 0.0 : (double)n * sizeof(Fr);
+        g_stats.d2h_bytes = d_a ? 0.0 : (double)n * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+}  // namespace eng
+}  // namespace b200

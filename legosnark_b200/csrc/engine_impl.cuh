@@ -392,7 +392,7 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         CK(cudaMemcpyAsync(D.bases_jac.p, bases, n * sizeof(Jacobian<F>), cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(D.ev[0], st));
         CK(cudaEventRecord(D.ev[2], st));
-        LAUNCH(D, (k_msm_small<F>), g.W, SMALL_THREADS, 0, st, D.bases_jac.as<Jacobian<F>>(), D.scalars.as<Fr>(), (uint32_t)n,
+        LAUNCH(D, (k_msm_small<F, Jacobian<F>>), g.W, SMALL_THREADS, 0, st, (const Jacobian<F> *)D.bases_jac.as<Jacobian<F>>(), D.scalars.as<Fr>(), (uint32_t)n,
                D.window_sums.as<XYZZ<F>>());
         CK(cudaEventRecord(D.ev[3], st));
         CK(cudaMemcpyAsync(D.h_pinned, D.window_sums.p, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
@@ -582,6 +582,30 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
                 ds = D.scalars.as<Fr>();
             }
             const Affine<F> *aff = reinterpret_cast<const Affine<F> *>(S.d_aff) + (P.lo - S.begin);
+            if (P.cnt <= SMALL_MAX_N && g_tune_c == 0) {
+                // one kernel on the resident affine bases (the small levels of CPPoly::prove, poly.h:77-88)
+                MsmGeom g;
+                g.c = SMALL_C;
+                g.W = g.Wb = SMALL_W;
+                g.B = SMALL_NBK;
+                g.NB = g.W * g.B;
+                g.pre_stride = g.pre_off = 0;
+                g.L = 0;
+                D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
+                D.totals.ensure(16);
+                D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
+                CK(cudaEventRecord(D.ev[0], st));
+                CK(cudaEventRecord(D.ev[2], st));
+                LAUNCH(D, (k_msm_small<F, Affine<F>>), g.W, SMALL_THREADS, 0, st, aff, ds, (uint32_t)P.cnt, D.window_sums.as<XYZZ<F>>());
+                CK(cudaEventRecord(D.ev[3], st));
+                CK(cudaMemsetAsync(D.totals.p, 0, 8, st));
+                CK(cudaMemcpyAsync(D.h_pinned, D.window_sums.p, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.W * sizeof(XYZZ<F>), D.totals.p, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaEventRecord(D.ev[1], st));
+                geoms[pi] = g;
+                CK(cudaStreamSynchronize(st));
+                return;
+            }
             // precomputed levels pay when this (sub-)range fills their one big bucket set
             bool pre = S.d_pre && g_tune_pre && g_tune_c == 0 && P.cnt > SMALL_MAX_N;
             if (pre && g_tune_pre != 2) {  // 2 = always (tests)

@@ -703,8 +703,31 @@ constexpr uint32_t SMALL_THREADS = 32 * SMALL_NBK;
 constexpr uint32_t SMALL_W = (255 + SMALL_C - 1) / SMALL_C;
 constexpr uint32_t SMALL_MAX_N = 4096;
 
+// the bases come as uploaded from the host (Jacobian, any Z) or from a resident key (affine)
 template <class F>
-__global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const Jacobian<F> *__restrict__ bases, const Fr *__restrict__ scalars_mont,
+__device__ __forceinline__ bool small_base_is_zero(const Jacobian<F> &p) { return p.z.is_zero(); }
+template <class F>
+__device__ __forceinline__ bool small_base_is_zero(const Affine<F> &p) { return p.is_inf(); }
+template <class F>
+__device__ __forceinline__ void small_base_add(XYZZ<F> &acc, Jacobian<F> p, bool neg)
+{
+    if (neg) p.y = F::neg(p.y);
+    if (p.z == F::one()) {
+        const Affine<F> a{p.x, p.y};
+        xyzz_madd_cold(&acc, &a, false);
+    } else {
+        const XYZZ<F> q = XYZZ<F>::from_jacobian(p);
+        xyzz_add_cold(&acc, &q);
+    }
+}
+template <class F>
+__device__ __forceinline__ void small_base_add(XYZZ<F> &acc, const Affine<F> &p, bool neg)
+{
+    xyzz_madd_cold(&acc, &p, neg);
+}
+
+template <class F, class BaseT>
+__global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const BaseT *__restrict__ bases, const Fr *__restrict__ scalars_mont,
                                                               uint32_t n, XYZZ<F> *__restrict__ window_sums)
 {
     __shared__ uint16_t sh_idx[SMALL_MAX_N];  // bucket-ordered point indices, bit 15 = negate
@@ -716,7 +739,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const Jacobian<F> *
     __syncthreads();
     for (uint32_t i = tid; i < n; i += SMALL_THREADS) {
         int d = 0;
-        if (!bases[i].z.is_zero()) {
+        if (!small_base_is_zero(bases[i])) {
             const Fr s = Fr::from_mont(scalars_mont[i]);
             for_each_digit(s, SMALL_C, SMALL_W, [&](uint32_t kk, uint32_t mag, uint32_t neg) {
                 if (kk == k) d = neg ? -(int)mag : (int)mag;
@@ -746,19 +769,10 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const Jacobian<F> *
     __syncthreads();
     // warp = bucket
     {
-        const F one = F::one();
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t e = sh_off[warp] + lane; e < sh_off[warp + 1]; e += 32) {
             const uint32_t ix = sh_idx[e];
-            Jacobian<F> p = bases[ix & 0x7fffu];
-            if (ix & 0x8000u) p.y = F::neg(p.y);
-            if (p.z == one) {
-                const Affine<F> a{p.x, p.y};
-                xyzz_madd_cold(&acc, &a, false);
-            } else {
-                const XYZZ<F> q = XYZZ<F>::from_jacobian(p);
-                xyzz_add_cold(&acc, &q);
-            }
+            small_base_add(acc, bases[ix & 0x7fffu], (ix & 0x8000u) != 0);
         }
         // shuffle tree only as deep as the bucket is full (tiny MSMs: 0-2 entries per bucket)
         const uint32_t m = sh_off[warp + 1] - sh_off[warp];

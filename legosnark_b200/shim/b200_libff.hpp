@@ -185,5 +185,56 @@ inline void to_special(std::vector<T> &vec)
     for (size_t i = 0; i < n; i++) vec[i] = point_from_limbs<T>(buf.data() + i * L);
 }
 
+// ---- Fr-side routines next to the MSMs: LegoSNARK callers -------------
+// MultiVPolyT::evalMLE (LS/prototools/polytools.h:207-234) on the device
+template <typename FieldT>
+inline FieldT eval_mle(const std::vector<FieldT> &v, const std::vector<FieldT> &r)
+{
+    static_assert(sizeof(FieldT) == 32, "unexpected scalar layout");
+    if (v.size() != ((size_t)1 << r.size())) throw std::runtime_error("evalMLE: expected N == 1 << d");  // polytools.h:211
+    ensure_init();
+    FieldT out;
+    check(b200_fr_eval_mle(reinterpret_cast<const uint64_t *>(v.data()), reinterpret_cast<const uint64_t *>(r.data()), r.size(),
+                           reinterpret_cast<uint64_t *>(&out)), "b200_fr_eval_mle");
+    return out;
+}
+
+// A commitment key kept on the device (CommScheme's g1s, LS/prototools/commit.h:129-147)
+template <typename T>
+struct resident_key {
+    uint64_t handle = 0;
+    size_t n = 0;
+    explicit resident_key(const std::vector<T> &bases) : n(bases.size())
+    {
+        static_assert(group_traits<T>::group == 0, "resident_key<T>: G1 keys (CPPoly::prove uses g1s)");
+        ensure_init();
+        if (b200_device_count() != 1)
+            throw std::runtime_error("resident_key: b200_cppoly_prove_g1 needs a single-device engine (set B200_GPUS=1)");
+        check(b200_pin_bases_g1(n ? limbs_of(bases.data()) : nullptr, n, &handle), "b200_pin_bases_g1");
+    }
+    ~resident_key()
+    {
+        if (handle) b200_unpin_bases(handle);
+    }
+    resident_key(const resident_key &) = delete;
+    resident_key &operator=(const resident_key &) = delete;
+};
+
+// CPPoly::prove (LS/gadgets/poly.h:45-91): witness[i] for i < d; witnessa[i] (i >= 1) equals witness[i]
+// in the reference too (same MSM over the same bases, poly.h:84-86).
+template <typename T, typename FieldT>
+inline std::vector<T> cppoly_prove(const resident_key<T> &key, const std::vector<FieldT> &v, const std::vector<FieldT> &r)
+{
+    static_assert(std::is_same<FieldT, typename T::scalar_field>::value && sizeof(FieldT) == 32, "scalars must be the group's Fr");
+    const size_t d = r.size();
+    if (v.size() != ((size_t)1 << d)) throw std::runtime_error("CPPoly::prove: expected v.size() == 1 << d");
+    std::vector<uint64_t> out(12 * d);
+    check(b200_cppoly_prove_g1(key.handle, reinterpret_cast<const uint64_t *>(v.data()), reinterpret_cast<const uint64_t *>(r.data()), d,
+                               out.data(), nullptr), "b200_cppoly_prove_g1");
+    std::vector<T> w(d, T::zero());
+    for (size_t i = 0; i < d; i++) w[i] = point_from_limbs<T>(out.data() + 12 * i);
+    return w;
+}
+
 }  // namespace b200shim
 #endif  // B200_LIBFF_HPP_

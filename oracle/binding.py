@@ -23,6 +23,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORC_PATH = os.path.join(HERE, "libbn254oracle.so")
 REF_PATH = os.path.join(HERE, "_ref", "libffref.so")
+LSREF_PATH = os.path.join(HERE, "_ref", "liblsref.so")  # oracle/ref_wrap_ls.cpp: LegoSNARK / libfqfft Fr-side routines
 
 _u64p = ctypes.POINTER(ctypes.c_uint64)
 
@@ -191,6 +192,81 @@ class Checker:
     def sha512_rng_fr(self, idx0, n):
         out = np.zeros((n, 4), dtype=np.uint64)
         self._call("sha512_rng_fr", ctypes.c_uint64(idx0), ctypes.c_size_t(n), _ptr(out))
+        return out
+
+    # -- Fr vector work next to the MSMs ----------------------
+    def _ls(self):
+        """Library holding the fr_* entry points: the restatement itself, or oracle/_ref/liblsref.so
+        (the reference's poly.h / polytools.h / mle.h / libfqfft behind oracle/ref_wrap_ls.cpp)."""
+        if self.kind == "orc":
+            return self.lib
+        if getattr(self, "_lslib", None) is None:
+            if not os.path.exists(LSREF_PATH) and os.path.isdir("/root/reference"):
+                build_ref()
+            if not os.path.exists(LSREF_PATH):
+                raise FileNotFoundError("oracle/_ref/liblsref.so not built (needs /root/reference)")
+            self._lslib = ctypes.CDLL(LSREF_PATH)
+            self._lslib.ref_ls_init()
+        return self._lslib
+
+    def _lscall(self, name, *args):
+        rc = getattr(self._ls(), self.p + name)(*args)
+        if rc != 0:
+            raise RuntimeError(f"{self.p}{name} returned {rc}")
+
+    def fr_eval_mle(self, v, r):
+        v, r = _c(v, 4), _c(r, 4)
+        d = r.shape[0]
+        assert v.shape[0] == 1 << d
+        out = np.zeros(4, dtype=np.uint64)
+        self._lscall("fr_eval_mle", _ptr(v), _ptr(r), ctypes.c_size_t(d), _ptr(out))
+        return out
+
+    def fr_fold_witness(self, v, r):
+        """(w_coeffs (2^d, 4), eval (4,)) of CPPoly::prove's folding; restatement only (the reference keeps
+        w_coeffs local to prove(): it is pinned through cppoly_prove_g1 and eval_mle)."""
+        assert self.kind == "orc"
+        v, r = _c(v, 4), _c(r, 4)
+        d = r.shape[0]
+        assert v.shape[0] == 1 << d
+        w = np.zeros((1 << d, 4), dtype=np.uint64)
+        ev = np.zeros(4, dtype=np.uint64)
+        self._lscall("fr_fold_witness", _ptr(v), _ptr(r), ctypes.c_size_t(d), _ptr(w), _ptr(ev))
+        return w, ev
+
+    def fr_mle_bind(self, table, r):
+        table, r = _c(table, 4), _c(r, 4)
+        half = table.shape[0] // 2
+        out = np.zeros((half, 4), dtype=np.uint64)
+        self._lscall("fr_mle_bind", _ptr(table), ctypes.c_size_t(half), _ptr(r), _ptr(out))
+        return out
+
+    def fr_fft(self, a, mode=0, g=None):
+        a = _c(a, 4).copy()
+        log_n = int(a.shape[0]).bit_length() - 1
+        assert a.shape[0] == 1 << log_n
+        g = None if g is None else _c(g, 4)
+        self._lscall("fr_fft", _ptr(a), ctypes.c_size_t(log_n), int(mode), _ptr(g))
+        return a
+
+    def cppoly_prove_g1(self, bases, v, r):
+        """CPPoly::prove's witness points (d, 12), affine-normalised.  ref: the reference class itself over
+        an installed key; orc: the restated folding + the restated multi_exp_with_mixed_addition."""
+        bases, v, r = _c(bases, 12), _c(v, 4), _c(r, 4)
+        d = r.shape[0]
+        out = np.zeros((d, 12), dtype=np.uint64)
+        if self.kind == "ref":
+            outa = np.zeros((d, 12), dtype=np.uint64)
+            self._lscall("cppoly_prove_g1", _ptr(bases), ctypes.c_size_t(bases.shape[0]), _ptr(v), _ptr(r), ctypes.c_size_t(d),
+                         _ptr(out), _ptr(outa))
+            assert (out == outa).all()  # witnessa repeats the MSM over the same bases (poly.h:84-86)
+            return out
+        w, _ = self.fr_fold_witness(v, r)
+        N = 1 << d
+        for i in range(d):
+            m = 1 << (d - i - 1)
+            start = N - 2 * m
+            out[i] = self.msm("g1", bases[:m], w[start:start + m], chunks=1, variant=1)
         return out
 
     def one(self, group):

@@ -497,6 +497,185 @@ int orc_sha512_rng_fr(uint64_t idx0, size_t n, uint64_t *out)
     return 0;
 }
 
+
+/* ------------------------------------------------------------------ */
+/* Fr vector work on either side of the MSMs */
+/* LS = src/, FQFFT = depends/libsnark/depends/libfqfft/libfqfft/         */
+/* ------------------------------------------------------------------ */
+static void fr_mul(fp_t *o, const fp_t *a, const fp_t *b) { fp_mul(o, a, b, &FR); }
+static void fr_add(fp_t *o, const fp_t *a, const fp_t *b) { fp_add(o, a, b, &FR); }
+static void fr_sub(fp_t *o, const fp_t *a, const fp_t *b) { fp_sub(o, a, b, &FR); }
+
+/* CPPoly::prove, witness coefficients: LS/gadgets/poly.h:45-67.
+ * w_coeffs has 2^d entries (zero-initialised, 2^d - 1 written); tmp_v ends with one value. */
+int orc_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval)
+{
+    const size_t N = (size_t)1 << d;
+    fp_t *tmp_v = (fp_t *)malloc(N * sizeof(fp_t));
+    fp_t *w = w_coeffs ? (fp_t *)w_coeffs : NULL;
+    const fp_t *rr = (const fp_t *)r;
+    if (!tmp_v) return 1;
+    memcpy(tmp_v, v, N * sizeof(fp_t));
+    if (w) memset(w, 0, N * sizeof(fp_t));
+    size_t start = 0;
+    for (size_t i = 0; i < d; i++) {
+        const size_t pBound = (size_t)1 << (d - i - 1);
+        fp_t r_minus_1;
+        fr_sub(&r_minus_1, &rr[i], &FR.one);
+        for (size_t p = 0; p < pBound; p++) {
+            const size_t p0 = p << 1, p1 = (p << 1) + 1;
+            fp_t neg0, a, b;
+            fp_neg(&neg0, &tmp_v[p0], &FR);
+            if (w) fr_add(&w[start + p], &neg0, &tmp_v[p1]);   /* -tmp_v[p0] + tmp_v[p1]              :57 */
+            fr_mul(&a, &neg0, &r_minus_1);                      /* -tmp_v[p0]*(r[i]-1) + tmp_v[p1]*r[i] :58 */
+            fr_mul(&b, &tmp_v[p1], &rr[i]);
+            fr_add(&tmp_v[p], &a, &b);
+        }
+        start += pBound;
+    }
+    if (eval) memcpy(eval, &tmp_v[0], sizeof(fp_t));
+    free(tmp_v);
+    return 0;
+}
+
+/* MultiVPolyT::evalMLE: LS/prototools/polytools.h:207-234 (table of the 2^d monomials, then a dot product) */
+int orc_fr_eval_mle(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *out)
+{
+    const size_t N = (size_t)1 << d;
+    fp_t *products = (fp_t *)malloc(N * sizeof(fp_t));
+    const fp_t *vv = (const fp_t *)v, *rr = (const fp_t *)r;
+    if (!products) return 1;
+    products[0] = FR.one;
+    size_t idx = 1;
+    for (size_t i = 0; i < d; i++) {
+        const size_t pBound = (size_t)1 << i;
+        fp_t one_minus_r;
+        fr_sub(&one_minus_r, &FR.one, &rr[i]);
+        for (size_t p = 0; p < pBound; p++) {
+            fr_mul(&products[p + idx], &products[p], &rr[i]);
+            fr_mul(&products[p], &products[p], &one_minus_r);
+        }
+        idx += (size_t)1 << i;
+    }
+    fp_t acc, t;
+    memset(&acc, 0, sizeof acc);
+    for (size_t p = 0; p < N; p++) {
+        fr_mul(&t, &vv[p], &products[p]);
+        fr_add(&acc, &acc, &t);
+    }
+    memcpy(out, &acc, sizeof acc);
+    free(products);
+    return 0;
+}
+
+/* DPMle::pushRandomness: LS/prototools/mle.h:199-210; eqbit(false, r) = 1 - r, eqbit(true, r) = r */
+int orc_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out)
+{
+    const fp_t *old = (const fp_t *)table, *rr = (const fp_t *)r;
+    fp_t *cur = (fp_t *)out;
+    fp_t one_minus_r;
+    fr_sub(&one_minus_r, &FR.one, rr);
+    for (size_t p = 0; p < half; p++) {
+        fp_t a, b;
+        fr_mul(&a, &old[p], &one_minus_r);
+        fr_mul(&b, &old[p + half], rr);
+        fr_add(&cur[p], &a, &b);
+    }
+    return 0;
+}
+
+/* Fr::root_of_unity, Fr::s = 28 (alt_bn128_init.cpp:57-60); get_root_of_unity: field_utils.tcc:38-51 */
+static void fr_root_of_unity(fp_t *omega, size_t logn)
+{
+    /* 19103219067921713944291392827692070036145651957329286315305642004821462161904 */
+    static const uint64_t ROOT[4] = {0x9bd61b6e725b19f0ULL, 0x402d111e41112ed4ULL, 0x00e0a7eb8ef62abcULL, 0x2a3c09f0a58a7e85ULL};
+    fp_from_bigint(omega, ROOT, &FR);
+    for (size_t i = 28; i > logn; --i) fr_mul(omega, omega, omega);
+}
+
+static void fr_pow_u64(fp_t *o, const fp_t *base, uint64_t e)
+{
+    fp_t r = FR.one, b = *base;
+    while (e) {
+        if (e & 1) fr_mul(&r, &r, &b);
+        fr_mul(&b, &b, &b);
+        e >>= 1;
+    }
+    *o = r;
+}
+
+/* _basic_serial_radix2_FFT: FQFFT/evaluation_domain/domains/basic_radix2_domain_aux.tcc:42-75 */
+static void fr_serial_radix2_fft(fp_t *a, size_t n, const fp_t *omega)
+{
+    const size_t logn = orc_log2(n);
+    for (size_t k = 0; k < n; ++k) {
+        size_t rk = 0;
+        for (size_t b = 0; b < logn; b++) rk |= ((k >> b) & 1) << (logn - 1 - b);  /* libff::bitreverse */
+        if (k < rk) {
+            const fp_t t = a[k];
+            a[k] = a[rk];
+            a[rk] = t;
+        }
+    }
+    size_t m = 1;
+    for (size_t s = 1; s <= logn; ++s) {
+        fp_t w_m;
+        fr_pow_u64(&w_m, omega, n / (2 * m));
+        for (size_t k = 0; k < n; k += 2 * m) {
+            fp_t w = FR.one;
+            for (size_t j = 0; j < m; ++j) {
+                fp_t t;
+                fr_mul(&t, &w, &a[k + j + m]);
+                fr_sub(&a[k + j + m], &a[k + j], &t);
+                fr_add(&a[k + j], &a[k + j], &t);
+                fr_mul(&w, &w, &w_m);
+            }
+        }
+        m *= 2;
+    }
+}
+
+/* _multiply_by_coset: basic_radix2_domain_aux.tcc:163-171 */
+static void fr_multiply_by_coset(fp_t *a, size_t n, const fp_t *g)
+{
+    fp_t u = *g;
+    for (size_t i = 1; i < n; ++i) {
+        fr_mul(&a[i], &a[i], &u);
+        fr_mul(&u, &u, g);
+    }
+}
+
+/* basic_radix2_domain<Fr>::FFT / iFFT / cosetFFT / icosetFFT: basic_radix2_domain.tcc:41-78.
+ * mode 0 FFT, 1 iFFT, 2 cosetFFT(g), 3 icosetFFT(g), 4 unscaled inverse; a has 2^log_n entries, in place. */
+int orc_fr_fft(uint64_t *a_, size_t log_n, int mode, const uint64_t *g_)
+{
+    fp_t *a = (fp_t *)a_;
+    const size_t n = (size_t)1 << log_n;
+    fp_t omega, g;
+    if (log_n < 1 || log_n > 28 || mode < 0 || mode > 4 || ((mode == 2 || mode == 3) && !g_)) return 1;
+    fr_root_of_unity(&omega, log_n);
+    if (g_) memcpy(&g, g_, sizeof g);
+    if (mode == 2) fr_multiply_by_coset(a, n, &g);
+    if (mode == 0 || mode == 2) {
+        fr_serial_radix2_fft(a, n, &omega);
+        return 0;
+    }
+    fp_t omega_inv, sconst, nn;
+    fp_inv(&omega_inv, &omega, &FR);
+    fr_serial_radix2_fft(a, n, &omega_inv);
+    if (mode == 4) return 0; /* _basic_radix2_FFT(a, omega.inverse()) alone: what extended / step domains call */
+    const uint64_t nb[4] = {(uint64_t)n, 0, 0, 0};
+    fp_from_bigint(&nn, nb, &FR);
+    fp_inv(&sconst, &nn, &FR);
+    for (size_t i = 0; i < n; ++i) fr_mul(&a[i], &a[i], &sconst);
+    if (mode == 3) {
+        fp_t ginv;
+        fp_inv(&ginv, &g, &FR);
+        fr_multiply_by_coset(a, n, &ginv);
+    }
+    return 0;
+}
+
 /* G1_one = (1,2,1): alt_bn128_init.cpp:148-150 ; G2_one: :209-213 */
 int orc_g1_one(uint64_t *out)
 {

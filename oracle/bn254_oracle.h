@@ -62,6 +62,17 @@ int orc_fq_from_bigint(const uint64_t *a, size_t n, uint64_t *out);
 
 int orc_sha512_rng_fr(uint64_t idx0, size_t n, uint64_t *out);
 
+/* Fr vector work next to the MSMs; the same functions are exported by
+ * oracle/ref_wrap_ls.cpp (prefix ref_) from the reference's own headers.
+ * fold: CPPoly::prove's w_coeffs + last tmp_v[0] (LS/gadgets/poly.h:45-67); eval_mle:
+ * MultiVPolyT::evalMLE (LS/prototools/polytools.h:207-234); mle_bind: DPMle::pushRandomness
+ * (LS/prototools/mle.h:199-210); fft: basic_radix2_domain<Fr> mode 0 FFT, 1 iFFT, 2 cosetFFT,
+ * 3 icosetFFT (FQFFT/evaluation_domain/domains/basic_radix2_domain.tcc). */
+int orc_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval);
+int orc_fr_eval_mle(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *out);
+int orc_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
+int orc_fr_fft(uint64_t *a, size_t log_n, int mode, const uint64_t *g);
+
 int orc_g1_one(uint64_t *out);
 int orc_g2_one(uint64_t *out);
 
