@@ -380,6 +380,15 @@ def main():
                "sample": f"first 2^{int(np.log2(m))} points of the workload, multi_exp<BDLO12> chunks={threads}, {dt:.2f} s; "
                          "GPU result on the same sample bit-identical"}
 
+    # ---- the other half of BASELINE.json's metric: cplink prove ms, from the end-to-end driver over the
+    # reference's own CPlink classes (integration/cplink_driver.cc; prebuilt binaries travel with the
+    # snapshot).  Run after the engine of this process is shut down; rank 0, N = 1 only.
+    key.close()
+    lb.shutdown()
+    cplink = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cplink = cplink_prove_ms()
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC.replace("g1", group), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -399,12 +408,35 @@ def main():
             "gpu_launches": int(stats["kernel_launches"]) * args.steps,
             "launches_per_step": int(stats["kernel_launches"]),
             "host_finalize_us": float(np.mean(fin_us)),
-            "roofline": roofline, "cpu_baseline": cpu, "plain_key": plain,
+            "roofline": roofline, "cpu_baseline": cpu, "plain_key": plain, "cplink": cplink,
         }), flush=True)
-    key.close()
-    lb.shutdown()
     if world > 1:
         dist.destroy_process_group()
+
+
+def cplink_prove_ms():
+    """src/examples/cplink at its shipped size (2^10, prove = one G1 MSM of 1026 points + the CPlink proof) through
+    the shim build and through the reference with OpenMP on; None when the drivers were not built."""
+    out = {}
+    for tag, exe in (("b200", "cplink_b200"), ("reference_omp", "cplink_cpuomp")):
+        path = os.path.join(ROOT, "integration", "_ref", exe)
+        if not os.path.exists(path):
+            return None
+        try:
+            env = dict(os.environ, B200_GPUS="1")
+            env.pop("OMP_NUM_THREADS", None)
+            r = subprocess.run([path, "10", "5"], capture_output=True, text=True, timeout=120, env=env)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            d = json.loads(line)
+            out[tag] = {"prove_ms": d["prove_ms_best"], "verified": d["verified"], "fingerprint": d["fingerprint"]}
+        except Exception as e:  # the headline numbers do not depend on this leg
+            out[tag] = {"error": str(e)[:200]}
+    try:
+        out["same_proof"] = out["b200"]["fingerprint"] == out["reference_omp"]["fingerprint"]
+    except Exception:
+        pass
+    out["what"] = "integration/cplink_driver.cc over the reference's CPlink classes, log2N = 10, best of 5 proves"
+    return out
 
 
 def stats2_bytes(st, k):
