@@ -7,7 +7,10 @@
  * point bit-for-bit against oracle/_ref/libffref.so (the unmodified reference
  * sources compiled in place) and tests/test_oracle_golden.py against the
  * fixtures in tests/golden/ that tools/make_golden.py produced from that same
- * reference build.
+ * reference build.  The Fr vector routines (fold / evalMLE / mle_bind / fft) are pinned
+ * the same way by tests/test_fr_vectors.py against oracle/_ref/liblsref.so (the reference's
+ * own classes behind oracle/ref_wrap_ls.cpp) and tests/golden/fr_vectors.npz
+ * (tools/make_golden_fr.py).
  *
  * All buffers: little-endian u64 limbs, Montgomery form with R = 2^256
  * (LFF/algebra/fields/fp.hpp:42).  G1 point = X|Y|Z = 12 limbs (Jacobian,
