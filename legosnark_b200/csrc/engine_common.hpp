@@ -85,7 +85,9 @@ struct Device {
     // sort
     DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, digits, meta, order, len_hist, len_cursor;
     // accumulation / reduction
-    DevBuf partial, seg_run, seg_acc, job_out, split, done, window_sums, bucket_sum;
+    DevBuf partial, seg_run, seg_acc, job_out, split, big, done, window_sums, bucket_sum;
+    // scalars equal to one, set aside by k_digit_count: index list, block partials, ticket, sum
+    DevBuf ones_idx, ones_part, ones_done, ones_sum;
     // batch_exp
     DevBuf out_jac, out_norm, coeff;
     // Fr vector kernels (engine_fr.cu): ping-pong value buffers, challenge point, witness coefficients
@@ -108,7 +110,7 @@ struct Device {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
                          &entries, &digits, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
-                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w};
+                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -159,7 +161,7 @@ extern std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
 extern std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
-extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre;
+extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre, g_tune_ones;
 // set while the second MSM of a knowledge-commitment pair runs: every device still holds the
 // scalars of its shard in D.scalars from the first one, so the host-buffer paths skip that upload
 extern bool g_scalars_resident;

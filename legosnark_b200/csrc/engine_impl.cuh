@@ -50,6 +50,7 @@ inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride
     g.Wb = pre_c ? 1 : g.W;
     g.pre_stride = pre_c ? pre_stride : 0;
     g.pre_off = pre_c ? pre_off : 0;
+    g.ones = g_tune_ones ? 1 : 0;
     g.NB = g.Wb * g.B;
     if (g_tune_L > 0) {
         g.L = (uint32_t)std::min(std::max(g_tune_L, 1), 1023);
@@ -191,7 +192,7 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.cursor.ensure((size_t)g.NB * 4);
     D.toff.ensure((size_t)g.NB * 4);
     D.tile_sums.ensure((size_t)P.ntiles * sizeof(uint2));
-    D.totals.ensure(16);
+    D.totals.ensure(32);
     D.entries.ensure(P.max_entries * 4);
     D.digits.ensure((size_t)g.W * ((chunk_max + 3) & ~(size_t)3) * 4);
     D.meta.ensure(P.max_tasks * sizeof(uint2));
@@ -203,23 +204,34 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.seg_acc.ensure(P.nseg * sizeof(XYZZ<F>));
     D.job_out.ensure((size_t)g.Wb * (P.njobs + 1) * P.split * sizeof(XYZZ<F>));
     D.split.ensure(std::min<size_t>(g.NB, P.max_tasks) * 4 + 4);
+    D.big.ensure(std::min<size_t>(g.NB, P.max_tasks / BIG_TASKS + 1) * 4 + 4);
     if (dense) D.bucket_sum.ensure((size_t)g.NB * sizeof(XYZZ<F>));
     if (D.done.cap < (size_t)g.Wb * 4) {
         D.done.ensure(1024 * 4);
         CK(cudaMemsetAsync(D.done.p, 0, D.done.cap, st));  // k_reduce_bits leaves the counters at zero
     }
     D.window_sums.ensure((size_t)g.Wb * sizeof(XYZZ<F>));
-    D.ensure_pinned((size_t)g.Wb * sizeof(XYZZ<F>) + 64);
+    D.ensure_pinned((size_t)(g.Wb + 2) * sizeof(XYZZ<F>) + 64);
+    if (g.ones) {
+        D.ones_idx.ensure(chunk_max * 4);
+        D.ones_part.ensure((size_t)D.sms * 2 * sizeof(XYZZ<F>));
+        D.ones_sum.ensure(sizeof(XYZZ<F>));
+        if (!D.ones_done.p) {
+            D.ones_done.ensure(4);
+            CK(cudaMemsetAsync(D.ones_done.p, 0, 4, st));  // k_sum_ones leaves the ticket at zero
+        }
+    }
     return P;
 }
 
 // bucket sort of the digits of `n` scalars and accumulation of the bucket (task) sums into D.partial
 template <class F>
 void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const Affine<F> *d_aff, const uint8_t *d_flags,
-                             const Fr *d_scalars, size_t n)
+                             const Fr *d_scalars, size_t n, bool first_chunk = true)
 {
     const MsmGeom &g = P.g;
     CK(cudaMemsetAsync(D.cnt.p, 0, (size_t)g.NB * 4, st));
+    CK(cudaMemsetAsync((char *)D.totals.p + 12, 0, 4, st));  // totals[3]: scalars equal to one
     CK(cudaMemsetAsync(D.len_hist.p, 0, (size_t)(g.L + 1) * 4, st));
 
     uint32_t *cnt = D.cnt.as<uint32_t>(), *off = D.off.as<uint32_t>(), *cursor = D.cursor.as<uint32_t>();
@@ -230,21 +242,34 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
 
     const uint32_t pblocks = cdiv(n, 256);
     const size_t dstride = (n + 3) & ~(size_t)3;
-    LAUNCH(D, k_digit_count, pblocks, 256, 0, st, d_scalars, d_flags, n, dstride, g, cnt, D.digits.as<uint32_t>());
+    LAUNCH(D, k_digit_count, pblocks, 256, 0, st, d_scalars, d_flags, n, dstride, g, cnt, D.digits.as<uint32_t>(),
+           g.ones ? D.ones_idx.as<uint32_t>() : (uint32_t *)nullptr, totals + 3);
     LAUNCH(D, k_scan_tile_sums, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums);
     LAUNCH(D, k_scan_tiles, 1, 1024, 0, st, tile_sums, P.ntiles, totals);
     LAUNCH(D, k_scan_apply, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
     LAUNCH(D, k_digit_scatter, dim3(cdiv(n, 1024), g.W), 256, 0, st, D.digits.as<uint32_t>(), n, dstride, g, cursor, entries);
     const size_t max_tasks = (size_t)g.W * n / g.L + g.NB;
     const uint32_t tblocks = cdiv(max_tasks, 256);
-    uint32_t *split = D.split.as<uint32_t>();
-    LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist, split);
+    uint32_t *split = D.split.as<uint32_t>(), *big = D.big.as<uint32_t>();
+    LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist, split, big);
     LAUNCH(D, k_len_scan, 1, 1024, 0, st, len_hist, len_cursor, g.L);
     LAUNCH(D, k_task_order, tblocks, 256, 2 * (g.L + 1) * 4, st, meta, totals, g, len_cursor, order);
     CK(cudaEventRecord(D.ev[2], st));
     LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
     CK(cudaEventRecord(D.ev[3], st));
     LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 8, 128, 0, st, cnt, toff, split, totals, g, partial);
+    {   // hot buckets: as many passes as the largest possible bucket (all tasks in one) needs; idle ones return at once
+        size_t reach = BIG_CHUNK;
+        for (uint32_t pass = 0;; pass++) {
+            LAUNCH(D, (k_big_combine<F>), (uint32_t)D.sms * 4, 128, 0, st, cnt, toff, big, totals, g, pass, partial);
+            if (reach >= max_tasks) break;
+            reach *= BIG_CHUNK;
+        }
+    }
+    if (g.ones)  // level 0 of a precomputed key starts at the table's base: this MSM's bases begin pre_off points in
+        LAUNCH(D, (k_sum_ones<F>), (uint32_t)D.sms * 2, ONES_THREADS, 0, st, d_aff + (g.pre_stride ? g.pre_off : 0),
+               (const uint32_t *)D.ones_idx.as<uint32_t>(), (const uint32_t *)(totals + 3), D.ones_part.as<XYZZ<F>>(),
+               D.ones_done.as<uint32_t>(), first_chunk, D.ones_sum.as<XYZZ<F>>());
 }
 
 template <class F>
@@ -266,6 +291,9 @@ void enqueue_reduce(Device &D, cudaStream_t st, const MsmPlan &P, bool dense)
            P.split, D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
     CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)g.Wb * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.Wb * sizeof(XYZZ<F>), D.totals.p, 8, cudaMemcpyDeviceToHost, st));
+    if (g.ones)
+        CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)(g.Wb + 1) * sizeof(XYZZ<F>), D.ones_sum.p, sizeof(XYZZ<F>),
+                           cudaMemcpyDeviceToHost, st));
 }
 
 // the whole MSM over bases and scalars that are already on the device; window sums land in D.h_pinned
@@ -328,7 +356,7 @@ MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *
         CK(cudaStreamWaitEvent(st, D.ev_ready[j], 0));
         run_ingest<F, false>(D, st, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
         enqueue_sort_accumulate<F>(D, st, P, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, D.scalars.as<Fr>() + lo,
-                                   cnt);
+                                   cnt, j == 0);
         enqueue_fold<F>(D, st, P, j == 0);
     }
     enqueue_reduce<F>(D, st, P, true);
@@ -352,6 +380,10 @@ host::HJac<typename HostOf<F>::type> finalize_windows(const Device &D, const Msm
         if (!acc.is_inf())
             for (uint32_t i = 0; i < g.c; i++) acc = host::jac_dbl(acc);
         acc = host::jac_add(acc, host::jac_from_xyzz(ws[k].x, ws[k].y, ws[k].zz, ws[k].zzz));
+    }
+    if (g.ones) {  // the bases with scalar one, summed by k_sum_ones (weight 1)
+        const HX &o = ws[g.Wb + 1];
+        acc = host::jac_add(acc, host::jac_from_xyzz(o.x, o.y, o.zz, o.zzz));
     }
     return acc;
 }
@@ -381,7 +413,7 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         g.B = SMALL_NBK;
         g.NB = g.W * g.B;
         g.Wb = g.W;
-        g.pre_stride = g.pre_off = 0;
+        g.pre_stride = g.pre_off = g.ones = 0;
         g.L = 0;
         D.scalars.ensure(n * sizeof(Fr));
         D.bases_jac.ensure(n * sizeof(Jacobian<F>));
@@ -589,10 +621,10 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
                 g.W = g.Wb = SMALL_W;
                 g.B = SMALL_NBK;
                 g.NB = g.W * g.B;
-                g.pre_stride = g.pre_off = 0;
+                g.pre_stride = g.pre_off = g.ones = 0;
                 g.L = 0;
                 D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
-                D.totals.ensure(16);
+                D.totals.ensure(32);
                 D.ensure_pinned((size_t)g.W * sizeof(XYZZ<F>) + 64);
                 CK(cudaEventRecord(D.ev[0], st));
                 CK(cudaEventRecord(D.ev[2], st));

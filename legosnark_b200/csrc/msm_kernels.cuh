@@ -46,6 +46,7 @@ struct MsmGeom {
     uint32_t Wb;          // windows of buckets: W, or 1 for a precomputed key
     uint32_t pre_stride;  // points per level of the precomputed table (0: plain key)
     uint32_t pre_off;     // first point of this MSM inside its level
+    uint32_t ones;        // 1: scalars equal to one were set aside by k_digit_count and summed by k_sum_ones
 };
 __host__ __device__ __forceinline__ uint32_t bucket_base(const MsmGeom &g, uint32_t k) { return g.pre_stride ? 0u : k * g.B; }
 
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(128) k_key_level(const Affine<F> *__restrict__
 // signed-digit recoding
 // ------------------------------------------------------------------------------
 template <class Fn>
-__device__ __forceinline__ void for_each_digit(const Fr &s, uint32_t c, uint32_t W, Fn fn)
+__device__ __forceinline__ void for_each_window(const Fr &s, uint32_t c, uint32_t W, Fn fn)
 {
     uint32_t limbs[9];
 #pragma unroll
@@ -157,32 +158,76 @@ __device__ __forceinline__ void for_each_digit(const Fr &s, uint32_t c, uint32_t
             neg = 0;
             carry = 0;
         }
-        if (mag) fn(k, mag, neg);
+        fn(k, mag, neg);  // every window, mag == 0: nothing to add
     }
+}
+
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const Fr &s, uint32_t c, uint32_t W, Fn fn)
+{
+    for_each_window(s, c, W, [&](uint32_t k, uint32_t mag, uint32_t neg) {
+        if (mag) fn(k, mag, neg);
+    });
+}
+
+// Histogram / cursor atomics of one warp on (mostly) distinct buckets go out one per lane.  When many
+// lanes of the warp hit the SAME bucket -- small scalars put half of all points into the carry bucket
+// (k, 1) of the first empty window, equal scalars put everything into one bucket per window -- the
+// same-address atomics serialise in L2.  All 32 lanes call this with their bucket (or NO_BUCKET):
+// a cheap neighbour test (one shuffle, one ballot; never fires on uniform digits) switches the warp
+// to match_any aggregation: one atomic per distinct bucket, ranks by popc.  Returns the lane's slot.
+constexpr uint32_t NO_BUCKET = 0xffffffffu;
+__device__ __forceinline__ uint32_t warp_bucket_add(uint32_t *__restrict__ counters, uint32_t bucket)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nb = __shfl_down_sync(0xffffffffu, bucket, 1);
+    const uint32_t dup = __ballot_sync(0xffffffffu, bucket != NO_BUCKET && lane < 31u && bucket == nb);
+    if (__popc(dup) < 2) return bucket != NO_BUCKET ? atomicAdd(&counters[bucket], 1u) : 0u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
+    const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+    uint32_t base = 0;
+    if (bucket != NO_BUCKET && lane == leader) base = atomicAdd(&counters[bucket], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
 }
 
 // Pass 1: one thread per point.  The scalar leaves Montgomery form once, its W signed digits are
 // counted into the bucket histogram and stored window-major, digits[k * stride + i] = |d| | sign << 31
 // (0 = nothing to add), so that pass 2 streams them back coalesced.
+// Scalars equal to ONE never enter the sort (ones_idx != nullptr): like the reference's
+// multi_exp_with_mixed_addition, which adds those bases directly (multiexp.tcc:455-487; 0/1-heavy
+// witness vectors are the common LegoSNARK / Groth16 input), their indices are appended to a list --
+// one ballot and one atomic per warp -- and summed by k_sum_ones; in the sort they would all hit
+// bucket 1 of window 0 (n same-address atomics, one giant bucket).
 static __global__ void __launch_bounds__(256) k_digit_count(const Fr *__restrict__ scalars_mont, const uint8_t *__restrict__ flags,
                                                       size_t n, size_t stride, MsmGeom g, uint32_t *__restrict__ cnt,
-                                                      uint32_t *__restrict__ digits)
+                                                      uint32_t *__restrict__ digits, uint32_t *__restrict__ ones_idx,
+                                                      uint32_t *__restrict__ ones_cnt)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flags[i]) {
-        for (uint32_t k = 0; k < g.W; k++) digits[(size_t)k * stride + i] = 0;
-        return;
+    const bool inrange = i < n;
+    const bool live = inrange && !flags[i];
+    Fr s = Fr::zero();
+    if (live) s = Fr::from_mont(scalars_mont[i]);
+    bool one = false;
+    if (ones_idx) {  // every lane of the warp takes part in the ballot
+        one = live && s.l[0] == 1u && (s.l[1] | s.l[2] | s.l[3] | s.l[4] | s.l[5] | s.l[6] | s.l[7]) == 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, one);
+        if (m) {
+            const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs(m) - 1u;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(ones_cnt, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (one) ones_idx[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
     }
-    const Fr s = Fr::from_mont(scalars_mont[i]);
-    uint32_t next = 0;  // windows below `next` have been written
-    for_each_digit(s, g.c, g.W, [&](uint32_t k, uint32_t mag, uint32_t neg) {
-        for (; next < k; next++) digits[(size_t)next * stride + i] = 0;
-        digits[(size_t)k * stride + i] = mag | (neg << 31);
-        next = k + 1;
-        atomicAdd(&cnt[bucket_base(g, k) + (mag - 1)], 1u);
+    // every lane walks all W windows (warp_bucket_add is warp-collective); lanes without a point, with a
+    // zero base or with a scalar set aside above carry s = 0: all digits zero
+    if (!live || one) s = Fr::zero();
+    for_each_window(s, g.c, g.W, [&](uint32_t k, uint32_t mag, uint32_t neg) {
+        if (inrange) digits[(size_t)k * stride + i] = mag ? (mag | (neg << 31)) : 0u;
+        warp_bucket_add(cnt, mag ? bucket_base(g, k) + (mag - 1) : NO_BUCKET);
     });
-    for (; next < g.W; next++) digits[(size_t)next * stride + i] = 0;
 }
 
 // Pass 2: grid (points / 4, windows), four consecutive digits per thread (one 128-bit load;
@@ -195,24 +240,25 @@ static __global__ void __launch_bounds__(256) k_digit_scatter(const uint32_t *__
 {
     const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const uint32_t k = blockIdx.y;
-    if (i0 >= n) return;
-    const uint4 v = *reinterpret_cast<const uint4 *>(digits + (size_t)k * stride + i0);
+    uint4 v = make_uint4(0, 0, 0, 0);  // lanes past the end stay for the warp-collective cursor update
+    if (i0 < n) v = *reinterpret_cast<const uint4 *>(digits + (size_t)k * stride + i0);
     const uint32_t d[4] = {v.x, v.y, v.z, v.w};
-    uint32_t pos[4];
     const uint32_t bb = bucket_base(g, k);
     const uint32_t pbase = g.pre_stride ? k * g.pre_stride + g.pre_off : 0u;  // level k of a precomputed key
 #pragma unroll
-    for (int t = 0; t < 4; t++)
-        if (d[t] && i0 + t < n) pos[t] = atomicAdd(&cursor[bb + ((d[t] & 0x7fffffffu) - 1)], 1u);
-#pragma unroll
-    for (int t = 0; t < 4; t++)
-        if (d[t] && i0 + t < n) entries[pos[t]] = (pbase + (uint32_t)(i0 + t)) | (d[t] & 0x80000000u);
+    for (int t = 0; t < 4; t++) {
+        const bool live = d[t] && i0 + t < n;
+        const uint32_t pos = warp_bucket_add(cursor, live ? bb + ((d[t] & 0x7fffffffu) - 1) : NO_BUCKET);
+        if (live) entries[pos] = (pbase + (uint32_t)(i0 + t)) | (d[t] & 0x80000000u);
+    }
 }
 
 // ------------------------------------------------------------------------------
 // exclusive scan over the bucket counts; element = (entries, tasks)
 // ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tasks_of(uint32_t cnt, uint32_t L) { return (cnt + L - 1) / L; }
+constexpr uint32_t BIG_TASKS = 32;     // buckets with more tasks than this are combined by k_big_combine
+constexpr uint32_t BIG_CHUNK = 1024;   // partials one warp sums per pass
 
 // phase 1: per-tile totals
 static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t *__restrict__ cnt, uint32_t NB, uint32_t L,
@@ -296,6 +342,7 @@ static __global__ void __launch_bounds__(1024) k_scan_tiles(uint2 *__restrict__ 
         totals[0] = carry_sm.x;  // total entries
         totals[1] = carry_sm.y;  // total tasks
         totals[2] = 0;           // number of split buckets (filled by k_task_meta)
+        totals[4] = 0;           // number of big buckets (more than BIG_TASKS tasks; filled by k_task_meta)
     }
 }
 
@@ -366,7 +413,7 @@ __device__ __forceinline__ uint32_t bucket_of_task(const uint32_t *__restrict__ 
 static __global__ void __launch_bounds__(256) k_task_meta(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off,
                                                     const uint32_t *__restrict__ toff, uint32_t *__restrict__ totals,
                                                     MsmGeom g, uint2 *__restrict__ meta, uint32_t *__restrict__ len_hist,
-                                                    uint32_t *__restrict__ split)
+                                                    uint32_t *__restrict__ split, uint32_t *__restrict__ big)
 {
     extern __shared__ uint32_t sh_hist[];  // L + 1 bins
     for (uint32_t k = threadIdx.x; k <= g.L; k += blockDim.x) sh_hist[k] = 0;
@@ -380,7 +427,10 @@ static __global__ void __launch_bounds__(256) k_task_meta(const uint32_t *__rest
         const uint32_t len = rem < g.L ? rem : g.L;
         meta[t] = make_uint2(off[b] + j * g.L, len);
         atomicAdd(&sh_hist[len], 1u);
-        if (j == 0 && cnt[b] > g.L) split[atomicAdd(&totals[2], 1u)] = b;  // bucket spans several tasks
+        if (j == 0 && cnt[b] > g.L) {  // bucket spans several tasks
+            if (tasks_of(cnt[b], g.L) > BIG_TASKS) big[atomicAdd(&totals[4], 1u)] = b;
+            else split[atomicAdd(&totals[2], 1u)] = b;
+        }
     }
     __syncthreads();
     for (uint32_t k = threadIdx.x; k <= g.L; k += blockDim.x)
@@ -494,11 +544,10 @@ __device__ __forceinline__ XYZZ<F> warp_sum_point(XYZZ<F> v, int width = 32)
     return v;  // lane 0 holds the sum
 }
 
-// buckets that were split into several tasks (listed by k_task_meta): their task partials are
+// buckets that were split into 2..BIG_TASKS tasks (listed by k_task_meta): their task partials are
 // summed into the bucket's first slot.  Four lanes serve one bucket (eight buckets per warp and
-// step: the common case is 2-3 partials, e.g. the short top window); buckets with more than 32
-// partials (a hot bucket: many equal scalars) are then served by the whole warp, one at a time.
-// With nothing split the kernel returns at once.
+// step: the common case is 2-3 partials, e.g. the short top window).  With nothing split the
+// kernel returns at once.
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_combine(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
                                                          const uint32_t *__restrict__ split, const uint32_t *__restrict__ totals,
@@ -514,35 +563,57 @@ __global__ void __launch_bounds__(128) k_bucket_combine(const uint32_t *__restri
         const uint32_t b = live ? split[i] : 0u;
         const uint32_t nt = live ? tasks_of(cnt[b], g.L) : 0u;
         const uint32_t t0 = live ? toff[b] : 0u;
-        const bool big = nt > 32;
         XYZZ<F> acc = XYZZ<F>::inf();
-        if (!big)
-            for (uint32_t k = sl; k < nt; k += 4) {
-                const XYZZ<F> q = partial[t0 + k];
+        for (uint32_t k = sl; k < nt; k += 4) {
+            const XYZZ<F> q = partial[t0 + k];
+            xyzz_add_cold(&acc, &q);
+        }
+        XYZZ<F> other = shfl_down_point(acc, 2);
+        if (sl < 2) xyzz_add_cold(&acc, &other);
+        other = shfl_down_point(acc, 1);
+        if (sl == 0) xyzz_add_cold(&acc, &other);
+        if (live && sl == 0) partial[t0] = acc;
+    }
+}
+
+// Hot buckets (more than BIG_TASKS tasks: a bucket that received a large share of ALL points -- equal
+// scalars, the carry bucket of small scalars, an almost empty top window on a precomputed key).  Pass p
+// works on the partials at stride BIG_CHUNK^p: every warp of the grid takes chunks of BIG_CHUNK of them
+// (any bucket), sums them (lanes stride, then a shuffle tree) and leaves the chunk sum in the chunk's
+// first slot; after ceil(log_BIG_CHUNK(tasks)) passes the bucket sum sits in its first slot, where the
+// window reduction expects it.  Passes are separate launches (grid-wide dependency).
+template <class F>
+__global__ void __launch_bounds__(128) k_big_combine(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
+                                                      const uint32_t *__restrict__ big, const uint32_t *__restrict__ totals,
+                                                      MsmGeom g, uint32_t pass, XYZZ<F> *__restrict__ partial)
+{
+    const uint32_t nbig = totals[4];
+    if (nbig == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    size_t stride = 1;
+    for (uint32_t p = 0; p < pass; p++) stride *= BIG_CHUNK;
+    uint32_t first = 0;  // global chunk index of this bucket's first chunk: chunks are dealt round-robin over all buckets
+    for (uint32_t bi = 0; bi < nbig; bi++) {
+        const uint32_t b = big[bi];
+        const size_t nt = tasks_of(cnt[b], g.L);
+        const size_t count = (nt + stride - 1) / stride;  // partials still standing at this pass
+        if (count <= 1) continue;
+        const uint32_t chunks = (uint32_t)((count + BIG_CHUNK - 1) / BIG_CHUNK);
+        const size_t t0 = toff[b];
+        for (uint32_t j = (warp + nwarps - first % nwarps) % nwarps; j < chunks; j += nwarps) {
+            const size_t m0 = (size_t)j * BIG_CHUNK, m1 = min(m0 + BIG_CHUNK, count);
+            XYZZ<F> acc = XYZZ<F>::inf();
+            for (size_t m = m0 + lane; m < m1; m += 32) {
+                const XYZZ<F> q = partial[t0 + m * stride];
                 xyzz_add_cold(&acc, &q);
             }
-        {
-            XYZZ<F> other = shfl_down_point(acc, 2);
-            if (sl < 2) xyzz_add_cold(&acc, &other);
-            other = shfl_down_point(acc, 1);
-            if (sl == 0) xyzz_add_cold(&acc, &other);
-        }
-        if (live && !big && sl == 0) partial[t0] = acc;
-        uint32_t pending = __ballot_sync(0xffffffffu, big && sl == 0);
-        while (pending) {
-            const int src = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const uint32_t ntb = __shfl_sync(0xffffffffu, nt, src);
-            const uint32_t tb = __shfl_sync(0xffffffffu, t0, src);
-            XYZZ<F> wacc = XYZZ<F>::inf();
-            for (uint32_t k = lane; k < ntb; k += 32) {
-                const XYZZ<F> q = partial[tb + k];
-                xyzz_add_cold(&wacc, &q);
-            }
-            wacc = warp_sum_point(wacc);
-            if (lane == 0) partial[tb] = wacc;
+            acc = warp_sum_point(acc);
+            if (lane == 0) partial[t0 + m0 * stride] = acc;
             __syncwarp();
         }
+        first += chunks;
     }
 }
 
@@ -628,6 +699,61 @@ __device__ __forceinline__ XYZZ<F> block_sum_point(XYZZ<F> v, XYZZ<F> *sm)
         v = warp_sum_point(v, (int)(blockDim.x >> 5));  // blockDim.x / 32 is a power of two
     }
     return v;  // thread 0 holds the block's sum
+}
+
+// Sum of the bases whose scalar is one (list built by k_digit_count).  Every thread adds its strided
+// share with mixed additions, blocks tree-sum, the last block to finish sums the block results
+// into `out` (first == false: adds to what an earlier chunk of a pipelined MSM left there).
+constexpr int ONES_THREADS = 128;
+template <class F>
+__global__ void __launch_bounds__(ONES_THREADS) k_sum_ones(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ ones_idx,
+                                                            const uint32_t *__restrict__ ones_cnt, XYZZ<F> *__restrict__ part,
+                                                            uint32_t *__restrict__ done, bool first, XYZZ<F> *__restrict__ out)
+{
+    __shared__ XYZZ<F> sm[ONES_THREADS / 32];
+    __shared__ uint32_t ticket;
+    const uint32_t count = *ones_cnt;
+    if (count == 0) {
+        if (first && blockIdx.x == 0 && threadIdx.x == 0) *out = XYZZ<F>::inf();
+        return;
+    }
+    // no more blocks than the list can feed (the others leave at once and take no ticket)
+    const uint32_t nblocks = min(gridDim.x, (count + ONES_THREADS - 1) / ONES_THREADS);
+    if (blockIdx.x >= nblocks) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t e = blockIdx.x * ONES_THREADS + threadIdx.x; e < count; e += nblocks * ONES_THREADS) {
+        const Affine<F> p = bases[ones_idx[e]];
+        xyzz_madd_cold(&acc, &p, false);
+    }
+    acc = block_sum_point(acc, sm);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = acc;
+        __threadfence();
+        ticket = atomicAdd(done, 1u);
+    }
+    __syncthreads();
+    if (ticket != nblocks - 1) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        XYZZ<F> v = XYZZ<F>::inf();
+        for (uint32_t o = threadIdx.x; o < nblocks; o += 32) {
+            const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(&part[o]);
+            XYZZ<F> q;
+            uint32_t *d = reinterpret_cast<uint32_t *>(&q);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = p[i];
+            xyzz_add_cold(&v, &q);
+        }
+        v = warp_sum_point(v);
+        if (threadIdx.x == 0) {
+            if (!first) {
+                const XYZZ<F> prev = *out;
+                xyzz_add_cold(&v, &prev);
+            }
+            *out = v;
+            *done = 0;  // ready for the next call
+        }
+    }
 }
 
 // grid ((njobs + 1) * RED2_SPLIT, W): job 0 sums twice as many points as the others and gets

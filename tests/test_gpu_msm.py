@@ -142,6 +142,38 @@ def test_precomputed_key(engine, orc, golden, grp, n):
         key.close()
 
 
+@pytest.mark.parametrize("grp,n", [("g1", 9000), ("g2", 5000)])
+def test_ones_filter(engine, orc, grp, n):
+    """Scalars equal to one are summed directly (multi_exp_with_mixed_addition's special addition,
+    multiexp.tcc:455-487) instead of going through the sort: same element with the filter on and off, with
+    zero bases and repeated bases among the ones, all-one scalars, and through the pipelined upload."""
+    P, _ = inputs.bases(orc, grp, n, seed=371, affine=False)
+    P[3] = inputs.zero_point(grp)
+    P[11] = P[10]
+    one = ints_to_mont([1], R_ORDER)[0]
+    cases = {"heavy": inputs.fr_zero_one_heavy(orc, n, seed=5), "all_one": np.tile(one, (n, 1)), "uniform": inputs.fr_uniform(orc, n, seed=372)}
+    cases["heavy"][0:16] = one
+    cases["uniform"][7] = one
+    key = engine.CommitmentKey(grp, P)
+    try:
+        for name, s in cases.items():
+            want = orc.msm(grp, P, s, chunks=orc.max_threads(), variant=1)
+            for ones in (1, 0):
+                engine.set_tuning_ex("ones_filter", ones)
+                assert (key.multi_exp(s) == want).all(), (name, ones, "resident")
+                assert (engine.multi_exp_with_mixed_addition(grp, P, s) == want).all(), (name, ones, "host")
+            engine.set_tuning_ex("ones_filter", 1)
+            engine.set_pipeline_chunks(3)
+            assert (engine.multi_exp(grp, P, s) == want).all(), (name, "chunks")
+            engine.set_pipeline_chunks(0)
+            m = n // 2
+            assert (key.multi_exp(s[:m], offset=100) == orc.msm(grp, P[100:100 + m], s[:m], chunks=orc.max_threads())).all()
+    finally:
+        engine.set_tuning_ex("ones_filter", 1)
+        engine.set_pipeline_chunks(0)
+        key.close()
+
+
 def _scalar_sum_expected(orc, grp, k, s):
     """(sum s_i k_i mod r) * G, with the big-integer sum vectorised over 64-bit limbs."""
     rinv = pow(MONT_R, -1, R_ORDER)
@@ -152,6 +184,42 @@ def _scalar_sum_expected(orc, grp, k, s):
 
     tot = sum(x * y for x, y in zip(to_ints(k), to_ints(s))) % R_ORDER
     return orc.scalar_mul(grp, orc.one(grp), ints_to_mont([tot], R_ORDER), normalise=True)[0]
+
+
+@pytest.mark.parametrize("grp,log2n", [("g1", 16), ("g2", 13)])
+def test_hot_buckets(engine, orc, grp, log2n):
+    """Buckets that receive a large share of all points: equal scalars (one bucket per window), 32-bit
+    scalars (rand32b of legogrothmatrix.cc:29-32: half of the points land in the carry bucket of the first
+    empty window), two-valued scalars.  Exercises the warp-aggregated histogram / cursor updates and the
+    multi-pass hot-bucket combine (forced tiny task lengths give thousands of partials per bucket), on the
+    plain and on a precomputed key; checked with the scalar-sum identity."""
+    n = 1 << log2n
+    k = inputs.fr_uniform(orc, n, seed=411)
+    table = engine.get_window_table(grp, 254, 0, orc.one(grp), expected_scalars=n)
+    P = engine.batch_exp(254, 0, table, k)
+    table.close()
+    rng = np.random.default_rng(3)
+    small = np.zeros((n, 4), dtype=np.uint64)
+    small[:, 0] = rng.integers(0, 1 << 32, size=n, dtype=np.uint64)
+    two = np.where((rng.random(n) < 0.5)[:, None], inputs.fr_uniform(orc, 1, seed=412), inputs.fr_uniform(orc, 1, seed=413))
+    cases = {"equal": np.tile(inputs.fr_uniform(orc, 1, seed=414), (n, 1)), "32bit": orc.fr_from_bigint(small), "two": two}
+    key = engine.CommitmentKey(grp, P)
+    try:
+        for name, s in cases.items():
+            want = _scalar_sum_expected(orc, grp, k, s)
+            for c, L in ((0, 0), (12, 4), (7, 1)):
+                engine.set_tuning(c, L)
+                assert (key.multi_exp(s) == want).all(), (name, c, L)
+            engine.set_tuning(0, 0)
+            assert (engine.multi_exp(grp, P, s) == want).all(), (name, "host")
+        key.precompute(11)
+        engine.set_tuning_ex("use_precomputed", 2)
+        for name, s in cases.items():
+            assert (key.multi_exp(s) == _scalar_sum_expected(orc, grp, k, s)).all(), (name, "precomputed")
+    finally:
+        engine.set_tuning(0, 0)
+        engine.set_tuning_ex("use_precomputed", 1)
+        key.close()
 
 
 @pytest.mark.parametrize("grp,log2n", [("g1", 18), ("g1", 20), ("g2", 16)])

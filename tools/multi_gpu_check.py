@@ -23,9 +23,22 @@ for g in (G, 1):
         out[grp + "_P"] = P
     o2, o1 = lb.kc_multi_exp(out["g2_P"], out["g1_P"][: n // 4], s[: n // 4])
     out["kc"] = np.concatenate([o2, o1])
+    # resident key sharded over the devices, plain and with the precomputed window multiples, full range and a sub-range
+    key = lb.CommitmentKey("g1", out["g1_P"])
+    out["pinned"] = key.multi_exp(s)
+    out["pinned_sub"] = key.multi_exp(s[: n // 2 + 5], offset=n // 4)
+    key.precompute()
+    t0 = time.perf_counter()
+    out["pinned_pre"] = key.multi_exp(s)
+    out["pre_ms"] = (time.perf_counter() - t0) * 1e3
+    out["pinned_pre_sub"] = key.multi_exp(s[: n // 2 + 5], offset=n // 4)
+    key.close()
+    assert (out["pinned"] == out["g1"]).all() and (out["pinned_pre"] == out["g1"]).all()
+    assert (out["pinned_sub"] == out["pinned_pre_sub"]).all()
     res[g] = out
     lb.shutdown()
-for key in ("g1", "g2", "kc", "g1_P", "g2_P"):
+for key in ("g1", "g2", "kc", "g1_P", "g2_P", "pinned", "pinned_sub", "pinned_pre", "pinned_pre_sub"):
     assert (res[G][key] == res[1][key]).all(), key
 print(f"multi-GPU in-process check ok: {G} devices == 1 device on MSM g1 2^{int(np.log2(n))} / g2 / kc / batch_exp; "
-      f"host-buffer g1 MSM {res[G]['g1_ms']:.2f} ms on {G} GPUs vs {res[1]['g1_ms']:.2f} ms on 1")
+      f"host-buffer g1 MSM {res[G]['g1_ms']:.2f} ms on {G} GPUs vs {res[1]['g1_ms']:.2f} ms on 1; "
+      f"precomputed resident key (host scalars) {res[G]['pre_ms']:.2f} ms vs {res[1]['pre_ms']:.2f} ms")
