@@ -3,6 +3,7 @@
 #include "engine_common.hpp"
 #include "field.cuh"
 #include "host_arith.hpp"
+#include "host_copy.hpp"
 #include "peak_kernels.cuh"
 
 namespace b200 {
@@ -30,6 +31,24 @@ uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1;
 bool g_scalars_resident = false;
+
+static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal
+static std::mutex g_stager_mu;
+Stager &stager_of(Device &D)
+{
+    std::lock_guard<std::mutex> lk(g_stager_mu);
+    auto &s = g_stagers[D.id];
+    if (!s) s = std::make_unique<Stager>();
+    return *s;
+}
+static void release_stagers()
+{
+    for (auto &kv : g_stagers) {
+        cudaSetDevice(kv.first);
+        kv.second->release();
+    }
+    g_stagers.clear();
+}
 
 std::vector<std::pair<size_t, size_t>> split_range(size_t n, size_t parts)
 {
@@ -162,6 +181,7 @@ void b200_shutdown(void)
         }
     g_tables.clear();
     fr_release();
+    release_stagers();
     for (auto &d : g_devs) d.release();
     g_devs.clear();
     g_init = false;

@@ -1,6 +1,7 @@
 // engine_fr.cu — host side of the Fr vector kernels (fr_kernels.cuh): multilinear folding
 // (CPPoly::prove / evalMLE / DPMle) and libfqfft's basic radix-2 domain.
 #include "engine_common.hpp"
+#include "host_copy.hpp"
 #include "fr_kernels.cuh"
 
 namespace b200 {
@@ -21,7 +22,7 @@ const void *fr_fold_device(Device &D, const uint64_t *v, const uint64_t *r, size
         // w_coeffs is a zero-initialised vector of 2^d entries of which 2^d - 1 are written (poly.h:52)
         CK(cudaMemsetAsync((char *)D.fr_w.p + (N - 1) * sizeof(Fr), 0, sizeof(Fr), st));
     }
-    CK(cudaMemcpyAsync(D.fr_a.p, v, N * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    h2d(D, D.fr_a.p, v, N * sizeof(Fr), st);
     if (d) CK(cudaMemcpyAsync(D.fr_r.p, r, d * sizeof(Fr), cudaMemcpyHostToDevice, st));
     Fr *cur = D.fr_a.as<Fr>(), *nxt = D.fr_b.as<Fr>();
     for (uint32_t i0 = 0; i0 < d;) {
@@ -46,7 +47,7 @@ int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_
         CK(cudaSetDevice(D.id));
         const size_t N = (size_t)1 << d;
         const void *fin = fr_fold_device(D, v, r, d, w_coeffs != nullptr);
-        if (w_coeffs) CK(cudaMemcpyAsync(w_coeffs, D.fr_w.p, N * sizeof(Fr), cudaMemcpyDeviceToHost, D.stream));
+        if (w_coeffs) d2h(D, w_coeffs, D.fr_w.p, N * sizeof(Fr), D.stream);
         if (eval) CK(cudaMemcpyAsync(eval, fin, sizeof(Fr), cudaMemcpyDeviceToHost, D.stream));
         CK(cudaStreamSynchronize(D.stream));
         g_stats = b200_stats_t{};
@@ -73,10 +74,10 @@ int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t 
         D.fr_a.ensure(2 * half * sizeof(Fr));
         D.fr_b.ensure(half * sizeof(Fr));
         D.fr_r.ensure(sizeof(Fr));
-        CK(cudaMemcpyAsync(D.fr_a.p, table, 2 * half * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        h2d(D, D.fr_a.p, table, 2 * half * sizeof(Fr), st);
         CK(cudaMemcpyAsync(D.fr_r.p, r, sizeof(Fr), cudaMemcpyHostToDevice, st));
         LAUNCH(D, k_fr_bind_hi, cdiv(half, 256), 256, 0, st, D.fr_a.as<Fr>(), half, D.fr_r.as<Fr>(), D.fr_b.as<Fr>());
-        CK(cudaMemcpyAsync(out, D.fr_b.p, half * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        d2h(D, out, D.fr_b.p, half * sizeof(Fr), st);
         CK(cudaStreamSynchronize(st));
         g_stats = b200_stats_t{};
         g_stats.n = half;
@@ -178,7 +179,7 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
             data = reinterpret_cast<Fr *>(d_a);
         } else {
             D.fr_a.ensure(n * sizeof(Fr));
-            CK(cudaMemcpyAsync(D.fr_a.p, a, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            h2d(D, D.fr_a.p, a, n * sizeof(Fr), st);
             data = D.fr_a.as<Fr>();
         }
         Fr *work = D.fr_b.as<Fr>();
@@ -216,7 +217,7 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
         }
         if (plan.size() == 1) CK(cudaMemcpyAsync(data, work, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
         if (!d_a) {
-            CK(cudaMemcpyAsync(a, data, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            d2h(D, a, data, n * sizeof(Fr), st);
             CK(cudaStreamSynchronize(st));
         }
         g_stats = b200_stats_t{};

@@ -3,6 +3,7 @@
 #pragma once
 #include "engine_common.hpp"
 #include "host_arith.hpp"
+#include "host_copy.hpp"
 #include "msm_kernels.cuh"
 #include "test_ops.cuh"
 
@@ -331,9 +332,8 @@ MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *
     cudaStream_t st = D.stream;
     const auto upload = [&](cudaStream_t cs, size_t lo, size_t cnt) {
         if (!g_scalars_resident)
-            CK(cudaMemcpyAsync(D.scalars.as<Fr>() + lo, scalars + lo * 4, cnt * sizeof(Fr), cudaMemcpyHostToDevice, cs));
-        CK(cudaMemcpyAsync(D.bases_jac.as<Jacobian<F>>() + lo, bases + lo * HostOf<F>::jac_limbs, cnt * sizeof(Jacobian<F>),
-                           cudaMemcpyHostToDevice, cs));
+            h2d(D, D.scalars.as<Fr>() + lo, scalars + lo * 4, cnt * sizeof(Fr), cs);
+        h2d(D, D.bases_jac.as<Jacobian<F>>() + lo, bases + lo * HostOf<F>::jac_limbs, cnt * sizeof(Jacobian<F>), cs);
     };
     if (S == 1) {
         upload(st, 0, n);
@@ -513,8 +513,7 @@ int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *h
                 LAUNCH(D, (k_affine_flags<F>), cdiv(S.count, 256), 256, 0, D.stream, (const Affine<F> *)S.d_aff, S.d_flags, S.count);
             } else {
                 D.bases_jac.ensure(S.count * sizeof(Jacobian<F>));
-                CK(cudaMemcpyAsync(D.bases_jac.p, bases + S.begin * HostOf<F>::jac_limbs, S.count * sizeof(Jacobian<F>),
-                                   cudaMemcpyHostToDevice, D.stream));
+                h2d(D, D.bases_jac.p, bases + S.begin * HostOf<F>::jac_limbs, S.count * sizeof(Jacobian<F>), D.stream);
                 run_ingest<F, false>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), S.d_aff, S.d_flags, S.count);
             }
             CK(cudaStreamSynchronize(D.stream));
@@ -610,7 +609,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
                 ds = reinterpret_cast<const Fr *>(d_scalars);
             } else {
                 D.scalars.ensure(P.cnt * sizeof(Fr));
-                CK(cudaMemcpyAsync(D.scalars.p, scalars + (P.lo - offset) * 4, P.cnt * sizeof(Fr), cudaMemcpyHostToDevice, st));
+                h2d(D, D.scalars.p, scalars + (P.lo - offset) * 4, P.cnt * sizeof(Fr), st);
                 ds = D.scalars.as<Fr>();
             }
             const Affine<F> *aff = reinterpret_cast<const Affine<F> *>(S.d_aff) + (P.lo - S.begin);
@@ -767,7 +766,7 @@ int batch_exp_table(uint64_t handle, const uint64_t *scalars, const void *d_scal
                 ds = reinterpret_cast<const Fr *>(d_scalars);
             } else {
                 D.scalars.ensure(m * sizeof(Fr));
-                CK(cudaMemcpyAsync(D.scalars.p, scalars + b * 4, m * sizeof(Fr), cudaMemcpyHostToDevice, st));
+                h2d(D, D.scalars.p, scalars + b * 4, m * sizeof(Fr), st);
                 ds = D.scalars.as<Fr>();
             }
             const Fr *dcoeff = nullptr;
@@ -784,7 +783,7 @@ int batch_exp_table(uint64_t handle, const uint64_t *scalars, const void *d_scal
             } else {
                 D.out_norm.ensure(m * sizeof(Jacobian<F>));
                 run_ingest<F, true>(D, st, D.out_jac.as<Jacobian<F>>(), D.out_norm.p, nullptr, m);
-                CK(cudaMemcpyAsync(out + b * HostOf<F>::jac_limbs, D.out_norm.p, m * sizeof(Jacobian<F>), cudaMemcpyDeviceToHost, st));
+                d2h(D, out + b * HostOf<F>::jac_limbs, D.out_norm.p, m * sizeof(Jacobian<F>), st);
                 CK(cudaStreamSynchronize(st));
             }
         });
@@ -832,9 +831,9 @@ int batch_to_affine(uint64_t *pts, size_t n)
             D.bases_jac.ensure(m * sizeof(Jacobian<F>));
             D.out_norm.ensure(m * sizeof(Jacobian<F>));
             uint64_t *hp = pts + b * HostOf<F>::jac_limbs;
-            CK(cudaMemcpyAsync(D.bases_jac.p, hp, m * sizeof(Jacobian<F>), cudaMemcpyHostToDevice, D.stream));
+            h2d(D, D.bases_jac.p, hp, m * sizeof(Jacobian<F>), D.stream);
             run_ingest<F, true>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), D.out_norm.p, nullptr, m);
-            CK(cudaMemcpyAsync(hp, D.out_norm.p, m * sizeof(Jacobian<F>), cudaMemcpyDeviceToHost, D.stream));
+            d2h(D, hp, D.out_norm.p, m * sizeof(Jacobian<F>), D.stream);
             CK(cudaStreamSynchronize(D.stream));
         });
         return B200_OK;

@@ -1,0 +1,164 @@
+// host_copy.hpp — large transfers between PAGEABLE host memory and the device.
+//
+// (COPY_THREADS below = copy_threads(), 4 unless B200_COPY_THREADS says otherwise.)
+// The reference's callers hold their vectors in ordinary std::vector storage; a plain
+// cudaMemcpyAsync from such memory is staged by the driver at 6-7 GB/s (measured on the B200 box:
+// 12 ms for the 32 MB in + 32 MB out of a 2^20 FFT), a fraction of what PCIe 5 x16 delivers.  Here
+// COPY_THREADS host threads each run their own double-buffered pipeline over an interleaved set of
+// 4 MB chunks: memcpy into a pinned buffer, cudaMemcpyAsync on a private stream, next chunk.  Memory
+// that is already page-locked (cudaHostAlloc / cudaHostRegister / torch pinned) and small transfers
+// go straight to cudaMemcpyAsync.
+//
+// Semantics match the pageable cudaMemcpyAsync they replace: h2d() returns once the source has been
+// read (the caller may reuse it), and `st` is ordered after the data has landed; d2h() returns when
+// the destination holds the data.
+#pragma once
+#include <cstdlib>
+
+#include "engine_common.hpp"
+
+namespace b200 {
+namespace eng {
+
+constexpr int COPY_THREADS_MAX = 8;
+constexpr size_t COPY_CHUNK = 4u << 20;
+// host threads per staged transfer: B200_COPY_THREADS (1..8; 0 = no staging, plain cudaMemcpyAsync), default 4
+inline int copy_threads()
+{
+    static const int n = [] {
+        const char *e = std::getenv("B200_COPY_THREADS");
+        const int v = e ? std::atoi(e) : 4;
+        return std::max(0, std::min(v, COPY_THREADS_MAX));
+    }();
+    return n;
+}
+constexpr size_t COPY_MIN_STAGED = 8u << 20;
+
+struct Stager {
+    void *pin[COPY_THREADS_MAX][2] = {};
+    cudaStream_t cs[COPY_THREADS_MAX] = {};
+    cudaEvent_t ev[COPY_THREADS_MAX][2] = {};
+    cudaEvent_t done[COPY_THREADS_MAX] = {};
+    cudaEvent_t gate = nullptr;
+    bool ready = false;
+    void init()
+    {
+        if (ready) return;
+        CK(cudaEventCreateWithFlags(&gate, cudaEventDisableTiming));
+        for (int t = 0; t < COPY_THREADS_MAX; t++) {
+            CK(cudaStreamCreateWithFlags(&cs[t], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&done[t], cudaEventDisableTiming));
+            for (int b = 0; b < 2; b++) {
+                CK(cudaHostAlloc(&pin[t][b], COPY_CHUNK, cudaHostAllocDefault));
+                CK(cudaEventCreateWithFlags(&ev[t][b], cudaEventDisableTiming));
+            }
+        }
+        ready = true;
+    }
+    void release()
+    {
+        if (!ready) return;
+        for (int t = 0; t < COPY_THREADS_MAX; t++) {
+            for (int b = 0; b < 2; b++) {
+                cudaFreeHost(pin[t][b]);
+                cudaEventDestroy(ev[t][b]);
+            }
+            cudaEventDestroy(done[t]);
+            cudaStreamDestroy(cs[t]);
+        }
+        cudaEventDestroy(gate);
+        ready = false;
+    }
+};
+
+Stager &stager_of(Device &D);  // engine_core.cu: one per device, created on first use, freed at shutdown
+
+inline bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+template <bool ToDevice>
+inline void staged_copy(Device &D, void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    Stager &S = stager_of(D);
+    S.init();
+    // the private streams start after whatever `st` still has in flight on these buffers
+    CK(cudaEventRecord(S.gate, st));
+    const size_t nchunks = (bytes + COPY_CHUNK - 1) / COPY_CHUNK;
+    std::vector<std::thread> th;
+    const int COPY_THREADS = copy_threads();
+    std::vector<std::string> errs(COPY_THREADS);
+    const int dev_id = D.id;
+    for (int t = 0; t < COPY_THREADS; t++)
+        th.emplace_back([&, t] {
+            try {
+                CK(cudaSetDevice(dev_id));
+                CK(cudaStreamWaitEvent(S.cs[t], S.gate, 0));
+                int b = 0;
+                size_t pending_off[2] = {0, 0}, pending_len[2] = {0, 0};
+                for (size_t c = (size_t)t; c < nchunks; c += COPY_THREADS, b ^= 1) {
+                    const size_t off = c * COPY_CHUNK, len = std::min(COPY_CHUNK, bytes - off);
+                    if (ToDevice) {
+                        CK(cudaEventSynchronize(S.ev[t][b]));  // the DMA that last read this pinned buffer is done
+                        memcpy(S.pin[t][b], (const char *)src + off, len);
+                        CK(cudaMemcpyAsync((char *)dst + off, S.pin[t][b], len, cudaMemcpyHostToDevice, S.cs[t]));
+                        CK(cudaEventRecord(S.ev[t][b], S.cs[t]));
+                    } else {
+                        if (pending_len[b]) {  // drain what this buffer received two chunks ago
+                            CK(cudaEventSynchronize(S.ev[t][b]));
+                            memcpy((char *)dst + pending_off[b], S.pin[t][b], pending_len[b]);
+                        }
+                        CK(cudaMemcpyAsync(S.pin[t][b], (const char *)src + off, len, cudaMemcpyDeviceToHost, S.cs[t]));
+                        CK(cudaEventRecord(S.ev[t][b], S.cs[t]));
+                        pending_off[b] = off;
+                        pending_len[b] = len;
+                    }
+                }
+                if (!ToDevice)
+                    for (int k = 0; k < 2; k++, b ^= 1)
+                        if (pending_len[b]) {
+                            CK(cudaEventSynchronize(S.ev[t][b]));
+                            memcpy((char *)dst + pending_off[b], S.pin[t][b], pending_len[b]);
+                            pending_len[b] = 0;
+                        }
+                CK(cudaEventRecord(S.done[t], S.cs[t]));
+            } catch (const CudaError &e) {
+                errs[t] = e.msg;
+            }
+        });
+    for (auto &x : th) x.join();
+    for (auto &e : errs)
+        if (!e.empty()) throw CudaError{e};
+    for (int t = 0; t < COPY_THREADS; t++) CK(cudaStreamWaitEvent(st, S.done[t], 0));
+}
+
+inline void h2d(Device &D, void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return;
+    if (bytes < COPY_MIN_STAGED || copy_threads() == 0 || !is_pageable(src)) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return;
+    }
+    staged_copy<true>(D, dst, src, bytes, st);
+}
+
+// returns with the data in dst only for the staged path; the direct path is asynchronous on `st` like
+// the call it replaces (every caller synchronises `st` before touching dst)
+inline void d2h(Device &D, void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return;
+    if (bytes < COPY_MIN_STAGED || copy_threads() == 0 || !is_pageable(dst)) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        return;
+    }
+    staged_copy<false>(D, dst, src, bytes, st);
+}
+
+}  // namespace eng
+}  // namespace b200
