@@ -68,19 +68,19 @@ inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride
     return g;
 }
 
-// window bits for extending a key of n bases (b200_key_precompute_*)
+// window bits for extending a key of n bases (b200_key_precompute_*), from the sweeps in
+// profiles/r09d_precompute_sweep_2p*.jsonl: c = 17 (255 = 15 x 17: a full top window) up to 2^18, 20 up
+// to 2^24, 22 beyond (the 2^21 buckets only pay off when W * n additions dominate).
 inline uint32_t choose_precompute_window(size_t n)
 {
-    uint32_t best_c = 8;
-    double best = 1e300;
-    for (uint32_t c = 8; c <= 22; c++) {
-        const double cost = geometry_cost(n, c, true);
-        if (cost < best) {
-            best = cost;
-            best_c = c;
-        }
-    }
-    return best_c;
+    return n < ((size_t)1 << 19) ? 17 : n < ((size_t)1 << 25) ? 20 : 22;
+}
+// a (sub-)range of a precomputed key takes the precomputed path when it fills the one big bucket set to
+// at least ~4 entries per bucket; shorter ranges run on the plain level-0 bases
+inline bool precomputed_pays(size_t n, uint32_t c)
+{
+    const double W = std::ceil(255.0 / c), B = (double)(1u << (c - 1));
+    return (double)n * W >= 4.0 * B;
 }
 
 template <class F>
@@ -639,10 +639,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
             }
             // precomputed levels pay when this (sub-)range fills their one big bucket set
             bool pre = S.d_pre && g_tune_pre && g_tune_c == 0 && P.cnt > SMALL_MAX_N;
-            if (pre && g_tune_pre != 2) {  // 2 = always (tests)
-                const MsmGeom plain = choose_geometry(P.cnt);
-                pre = geometry_cost(P.cnt, S.pre_c, true) < geometry_cost(P.cnt, plain.c, false);
-            }
+            if (pre && g_tune_pre != 2) pre = precomputed_pays(P.cnt, S.pre_c);  // 2 = always (tests)
             if (pre) {
                 const MsmGeom gp = choose_geometry(P.cnt, S.pre_c, (uint32_t)S.count, (uint32_t)(P.lo - S.begin));
                 geoms[pi] = enqueue_msm<F>(D, st, reinterpret_cast<const Affine<F> *>(S.d_pre), S.d_flags + (P.lo - S.begin), ds,

@@ -195,7 +195,60 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
         for (int i = 0; i < 8; i++) sm[i * E + e] = v.l[i];
     }
     __syncthreads();
-    for (uint32_t q = 0; q < P.k; q++) {
+    // two stages per trip through shared memory (radix 4 in registers): the thread owns the four
+    // elements whose `mid` differs in bits q and q + 1.  Stage q uses one twiddle for both of its
+    // butterflies (bit q + 1 lies above the stage), stage q + 1 uses two.
+    uint32_t q = 0;
+    for (; q + 1 < P.k; q += 2) {
+        const uint32_t sh_a = P.logn - (P.s0 + q) - 1;  // stage q exponent shift; stage q + 1: sh_a - 1
+        for (uint32_t g4 = threadIdx.x; g4 < (E >> 2); g4 += FFT_THREADS) {
+            const uint32_t l = g4 & tmask, rest = g4 >> P.t;
+            const uint32_t mid_lo = rest & ((1u << q) - 1u), mid_hi = rest >> q;
+            const uint32_t mid0 = (mid_hi << (q + 2)) | mid_lo;
+            const uint32_t e00 = (mid0 << P.t) | l, step = 1u << (q + P.t);
+            const uint32_t e01 = e00 + step, e10 = e00 + 2 * step, e11 = e00 + 3 * step;
+            const size_t ja = ((size_t)mid_lo << P.s0) + lo0 + l;        // idx mod 2^(s0+q)
+            const size_t jb1 = ja + ((size_t)1 << (P.s0 + q));             // idx mod 2^(s0+q+1) when bit q is set
+            Fr a00, a01, a10, a11;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                a00.l[i] = sm[i * E + e00];
+                a01.l[i] = sm[i * E + e01];
+                a10.l[i] = sm[i * E + e10];
+                a11.l[i] = sm[i * E + e11];
+            }
+            // stage q
+            if (ja) {
+                const Fr wa = tw[ja << sh_a];
+                a01 = Fr::mul(wa, a01);
+                a11 = Fr::mul(wa, a11);
+            }
+            Fr t = a01;
+            a01 = Fr::sub(a00, t);
+            a00 = Fr::add(a00, t);
+            t = a11;
+            a11 = Fr::sub(a10, t);
+            a10 = Fr::add(a10, t);
+            // stage q + 1: (a00, a10) with omega^(ja ...), (a01, a11) with omega^(jb1 ...)
+            if (ja) a10 = Fr::mul(tw[ja << (sh_a - 1)], a10);
+            a11 = Fr::mul(tw[jb1 << (sh_a - 1)], a11);
+            t = a10;
+            a10 = Fr::sub(a00, t);
+            a00 = Fr::add(a00, t);
+            t = a11;
+            a11 = Fr::sub(a01, t);
+            a01 = Fr::add(a01, t);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                sm[i * E + e00] = a00.l[i];
+                sm[i * E + e01] = a01.l[i];
+                sm[i * E + e10] = a10.l[i];
+                sm[i * E + e11] = a11.l[i];
+            }
+        }
+        __syncthreads();
+    }
+    for (; q < P.k; q++) {  // odd stage count: one radix-2 stage
         const uint32_t s = P.s0 + q;
         const uint32_t tw_shift = P.logn - s - 1;  // exponent = j * n / 2^(s+1)
         for (uint32_t bf = threadIdx.x; bf < (E >> 1); bf += FFT_THREADS) {
