@@ -505,16 +505,33 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict_
     const uint2 m = meta[t];
     const uint32_t *e = entries + m.x;
     XYZZ<F> acc = XYZZ<F>::inf();
-    uint32_t cur = e[0];
-    Affine<F> p = bases[cur & 0x7fffffffu];
-    for (uint32_t k = 0; k < m.y; k++) {
-        const uint32_t neg = cur >> 31;
-        const Affine<F> q = p;
-        if (k + 1 < m.y) {  // prefetch the next point while this one is added
-            cur = e[k + 1];
-            p = bases[cur & 0x7fffffffu];
+    if (sizeof(F) <= 32) {
+        // G1: the next point is loaded into registers while this one is added
+        uint32_t cur = e[0];
+        Affine<F> p = bases[cur & 0x7fffffffu];
+        for (uint32_t k = 0; k < m.y; k++) {
+            const uint32_t neg = cur >> 31;
+            const Affine<F> q = p;
+            if (k + 1 < m.y) {
+                cur = e[k + 1];
+                p = bases[cur & 0x7fffffffu];
+            }
+            xyzz_madd(acc, q.x, q.y, neg != 0);
         }
-        xyzz_madd(acc, q.x, q.y, neg != 0);
+    } else {
+        // G2: accumulator (64 registers) + one point (32) + the product temporaries already fill the
+        // register file; a second point in flight spills.  The next point (one 128-byte line) is
+        // pulled into L2 instead and loaded when its turn comes.
+        uint32_t cur = e[0];
+        for (uint32_t k = 0; k < m.y; k++) {
+            const uint32_t neg = cur >> 31;
+            const Affine<F> q = bases[cur & 0x7fffffffu];
+            if (k + 1 < m.y) {
+                cur = e[k + 1];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(bases + (cur & 0x7fffffffu)));
+            }
+            xyzz_madd(acc, q.x, q.y, neg != 0);
+        }
     }
     partial[t] = acc;
 }
