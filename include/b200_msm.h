@@ -180,6 +180,23 @@ int b200_fr_fft(uint64_t *a, size_t log_n, int mode, const uint64_t *coset_g /* 
 /* same, on a device-resident vector, enqueued on cuda_stream (bench.py / callers that chain transforms) */
 int b200_fr_fft_dev(void *d_a, size_t log_n, int mode, const uint64_t *coset_g, void *cuda_stream);
 
+/* ---- wire formats: point compression of the reference's stream operators ----
+ * operator<< / operator>> of alt_bn128_G1/G2 (alt_bn128_g1.cpp:404-459, alt_bn128_g2.cpp:414-475) and
+ * bn128_G1/G2 (bn128_g1.cpp:344-463, bn128_g2.cpp:374-470) with point compression (the default):
+ * a point is written as  is_zero | X | lsb(Y)  after to_affine_coordinates(), and read back as
+ * Y = +-sqrt(X^3 + b) with the sign picked by the stored bit.  The arithmetic (one shared inversion
+ * for the normalisation; one 252-bit Fq resp. 503-bit Fq2 exponentiation per point for the root) runs on
+ * the device; the byte framing ('0'/'1' characters, separators) is host work (shim: b200shim::write_points /
+ * read_points).  flavour 0: alt_bn128 (X in standard form, bit = lsb of Y.as_bigint()); 1: alt_bn128 with
+ * -DMONTGOMERY_OUTPUT (X Montgomery image); 2: bn128 -DBINARY_OUTPUT (raw Montgomery X, bit = lsb of Y's
+ * Montgomery image).  x: n x 4 (G1) / n x 8 (G2) limbs; flags[i]: bit 0 = the Y bit, bit 1 = is_zero.
+ * decompress writes (X, Y, 1) Montgomery Jacobian or (0, 1, 0); bad (may be NULL) gets 1 where X^3 + b is
+ * not a square -- with bad == NULL such input makes the call fail (the reference's sqrt would not return). */
+int b200_compress_g1(const uint64_t *pts /* n x 12 */, size_t n, int flavour, uint64_t *x_out, uint8_t *flags);
+int b200_compress_g2(const uint64_t *pts /* n x 24 */, size_t n, int flavour, uint64_t *x_out, uint8_t *flags);
+int b200_decompress_g1(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out /* n x 12 */, uint8_t *bad);
+int b200_decompress_g2(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out /* n x 24 */, uint8_t *bad);
+
 /* ---- parity hooks: element-wise kernels over the device arithmetic ------------
  * field: 0 Fq, 1 Fr, 2 Fq2.  op: 0 mul, 1 sqr, 2 add, 3 sub, 4 inverse, 5 neg,
  * 6 as_bigint (Fq/Fr), 7 from bigint (Fq/Fr).  b may be NULL for unary ops. */

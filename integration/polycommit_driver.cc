@@ -9,7 +9,10 @@
 //
 //   polycommit_{cpu,b200} [l = 12]
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
+#include <sstream>
+#include <string>
 #include <vector>
 using namespace std;
 
@@ -88,6 +91,40 @@ int main(int argc, char **argv)
     }
 #endif
 
+    // Persisting the key: the reference's `out << g1s` / `in >> g1s` against the device
+    // path producing / consuming the same bytes (first 2^16 bases: the reference's reader takes ~25 us per square root).
+    double ref_write_ms = -1, ref_read_ms = -1, dev_write_ms = -1, dev_read_ms = -1;
+    bool wire_same = true;
+    {
+        const vector<LG1> all = key.getBases1();
+        const vector<LG1> part(all.begin(), all.begin() + std::min<size_t>(all.size(), (size_t)1 << 16));
+        std::ostringstream ro;
+        t0 = now_ms();
+        ro << part;
+        ref_write_ms = now_ms() - t0;
+        const std::string image = ro.str();
+        std::istringstream ri(image);
+        vector<LG1> back;
+        t0 = now_ms();
+        ri >> back;
+        ref_read_ms = now_ms() - t0;
+        wire_same = back.size() == part.size();
+#ifdef B200_SHIM_MULTIEXP_HPP_
+        std::ostringstream go;
+        t0 = now_ms();
+        b200shim::write_points(go, part);
+        dev_write_ms = now_ms() - t0;
+        wire_same = wire_same && go.str() == image;
+        std::istringstream gi(image);
+        vector<LG1> gback;
+        t0 = now_ms();
+        b200shim::read_points(gi, gback);
+        dev_read_ms = now_ms() - t0;
+        wire_same = wire_same && gback.size() == back.size();
+        for (size_t i = 0; wire_same && i < back.size(); i++) wire_same = gback[i] == back[i];
+#endif
+    }
+
     harness::Fingerprint fp;
     fp.point(cm.c.c);
     fp.point(cm.c.kc);
@@ -97,13 +134,15 @@ int main(int argc, char **argv)
 
     printf("{\"example\": \"polycommit\", \"impl\": \"%s\", \"l\": %d, \"keygen_ms\": %.3f, \"commit_ms\": %.3f, "
            "\"answer_ms\": %.3f, \"prove_ms\": %.3f, \"proof_elems\": %zu, \"fingerprint\": \"%s\", "
-           "\"fused_answer_ms\": %.3f, \"fused_prove_ms\": %.3f, \"key_pin_ms\": %.3f, \"fused_same_proof\": %s}\n",
+           "\"fused_answer_ms\": %.3f, \"fused_prove_ms\": %.3f, \"key_pin_ms\": %.3f, \"fused_same_proof\": %s, "
+           "\"key_write_2p16_ms\": {\"reference\": %.3f, \"device\": %.3f}, \"key_read_2p16_ms\": {\"reference\": %.3f, \"device\": %.3f}, "
+           "\"wire_identical\": %s}\n",
 #ifdef B200_SHIM_MULTIEXP_HPP_
            "b200",
 #else
            "libff-cpu",
 #endif
            l, keygen_ms, commit_ms, answer_ms, prove_ms, pf.getSize(), fp.hex().c_str(), fused_answer_ms, fused_prove_ms, pin_ms,
-           fused_same ? "true" : "false");
+           fused_same ? "true" : "false", ref_write_ms, dev_write_ms, ref_read_ms, dev_read_ms, wire_same ? "true" : "false");
     return 0;
 }

@@ -355,6 +355,35 @@ def fr_fft_device(d_ptr: int, log_n: int, mode: int = FFT, g=None, stream: int =
     _check(lib().b200_fr_fft_dev(_vp(d_ptr), _sz(log_n), int(mode), None if g is None else _p(g), _vp(stream)), "b200_fr_fft_dev")
 
 
+# ---- wire format: point compression --------------------------------
+ALT_BN128, ALT_BN128_MONTGOMERY_OUTPUT, BN128 = 0, 1, 2
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def compress_points(group, pts, flavour: int = ALT_BN128):
+    """The arithmetic of the reference's compressed operator<< (alt_bn128_g1.cpp:404-419, bn128_g1.cpp:344-373):
+    (X in wire form (n, 4|8), flags (n,) uint8: bit 0 = Y bit, bit 1 = is_zero)."""
+    pts = _arr(pts, _LIMBS[group])
+    n = pts.shape[0]
+    x = np.zeros((n, _LIMBS[group] // 3), dtype=np.uint64)
+    flags = np.zeros(n, dtype=np.uint8)
+    _check(getattr(lib(), "b200_compress_" + group)(_p(pts), _sz(n), int(flavour), _p(x), flags.ctypes.data_as(_u8p)),
+           "b200_compress_" + group)
+    return x, flags
+
+
+def decompress_points(group, x, flags, flavour: int = ALT_BN128, report_bad: bool = False):
+    """operator>> with point compression (alt_bn128_g1.cpp:421-459): (X, Y, 1) with Y = +-sqrt(X^3 + b), or the zero."""
+    x = _arr(x, _LIMBS[group] // 3)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    n = x.shape[0]
+    out = np.zeros((n, _LIMBS[group]), dtype=np.uint64)
+    bad = np.zeros(n, dtype=np.uint8) if report_bad else None
+    _check(getattr(lib(), "b200_decompress_" + group)(_p(x), flags.ctypes.data_as(_u8p), _sz(n), int(flavour), _p(out),
+                                                      None if bad is None else bad.ctypes.data_as(_u8p)), "b200_decompress_" + group)
+    return (out, bad) if report_bad else out
+
+
 # ---- introspection ---------------------------------------------------------------------
 def last_stats() -> dict:
     s = Stats()

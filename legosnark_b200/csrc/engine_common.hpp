@@ -222,6 +222,11 @@ int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_
 int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
 int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, void *stream);
 void fr_release();
+// point (de)compression (engine_wire.cu)
+int compress_g1(const uint64_t *pts, size_t n, int fl, uint64_t *x, uint8_t *flags);
+int compress_g2(const uint64_t *pts, size_t n, int fl, uint64_t *x, uint8_t *flags);
+int decompress_g1(const uint64_t *x, const uint8_t *flags, size_t n, int fl, uint64_t *pts, uint8_t *bad);
+int decompress_g2(const uint64_t *x, const uint8_t *flags, size_t n, int fl, uint64_t *pts, uint8_t *bad);
 int cppoly_prove_g1(uint64_t key, const uint64_t *v, const uint64_t *r, size_t d, uint64_t *witness, uint64_t *eval);  // engine_g1.cu
 
 }  // namespace eng

@@ -385,6 +385,27 @@ int b200_fr_fft_dev(void *d_a, size_t log_n, int mode, const uint64_t *coset_g, 
     return fr_fft(nullptr, d_a, log_n, mode, coset_g, cuda_stream);
 }
 
+int b200_compress_g1(const uint64_t *pts, size_t n, int flavour, uint64_t *x_out, uint8_t *flags)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return compress_g1(pts, n, flavour, x_out, flags);
+}
+int b200_compress_g2(const uint64_t *pts, size_t n, int flavour, uint64_t *x_out, uint8_t *flags)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return compress_g2(pts, n, flavour, x_out, flags);
+}
+int b200_decompress_g1(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out, uint8_t *bad)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return decompress_g1(x, flags, n, flavour, pts_out, bad);
+}
+int b200_decompress_g2(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out, uint8_t *bad)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return decompress_g2(x, flags, n, flavour, pts_out, bad);
+}
+
 int b200_batch_to_affine_g1(uint64_t *pts, size_t n)
 {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -22,6 +22,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <istream>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -235,6 +237,76 @@ inline std::vector<T> cppoly_prove(const resident_key<T> &key, const std::vector
     for (size_t i = 0; i < d; i++) w[i] = point_from_limbs<T>(out.data() + 12 * i);
     return w;
 }
+
+// ---- wire format: std::vector<G> <-> the reference's stream image ---------------
+// Byte-identical to `out << vec` / `in >> vec` of the reference (alt_bn128_g1.cpp:461-497, bn128_g1.cpp:465-492 and
+// the G2 twins) for builds with -DBINARY_OUTPUT and point compression (LegoSNARK's configuration): the size line,
+// then per point  '0'|'1' (is_zero), X raw bytes, '0'|'1' (Y bit).  The normalisation, Montgomery conversions and
+// the square roots run on the device (b200_compress_* / b200_decompress_*); this is only the framing.
+#if defined(BINARY_OUTPUT) && !defined(NO_PT_COMPRESSION)
+template <typename T>
+struct wire_traits {
+    // bn128 writes the raw Montgomery image and takes the Y bit from it; alt_bn128 goes through as_bigint unless
+    // -DMONTGOMERY_OUTPUT (fp.tcc operator<<)
+    static int flavour()
+    {
+        if (std::is_same<T, libff::bn128_G1>::value || std::is_same<T, libff::bn128_G2>::value) return 2;
+#ifdef MONTGOMERY_OUTPUT
+        return 1;
+#else
+        return 0;
+#endif
+    }
+};
+
+template <typename T>
+inline void write_points(std::ostream &out, const std::vector<T> &v)
+{
+    ensure_init();
+    const size_t L = group_traits<T>::limbs, xb = L / 3 * 8, n = v.size();
+    out << n << "\n";
+    if (n == 0) return;
+    std::vector<uint64_t> x(n * L / 3);
+    std::vector<uint8_t> flags(n);
+    check(group_traits<T>::group == 0 ? b200_compress_g1(limbs_of(v.data()), n, wire_traits<T>::flavour(), x.data(), flags.data())
+                                      : b200_compress_g2(limbs_of(v.data()), n, wire_traits<T>::flavour(), x.data(), flags.data()),
+          "b200_compress");
+    std::string buf(n * (xb + 2), '0');
+    for (size_t i = 0; i < n; i++) {
+        char *p = &buf[i * (xb + 2)];
+        p[0] = (flags[i] & 2) ? '1' : '0';
+        std::memcpy(p + 1, reinterpret_cast<const char *>(x.data()) + i * xb, xb);
+        p[xb + 1] = (flags[i] & 1) ? '1' : '0';
+    }
+    out.write(buf.data(), (std::streamsize)buf.size());
+}
+
+template <typename T>
+inline void read_points(std::istream &in, std::vector<T> &v)
+{
+    ensure_init();
+    const size_t L = group_traits<T>::limbs, xb = L / 3 * 8;
+    size_t n = 0;
+    in >> n;
+    in.get();  // the newline after the size (consume_newline)
+    v.assign(n, T::zero());
+    if (n == 0) return;
+    std::string buf(n * (xb + 2), '\0');
+    in.read(&buf[0], (std::streamsize)buf.size());
+    if ((size_t)in.gcount() != buf.size()) throw std::runtime_error("read_points: stream ended early");
+    std::vector<uint64_t> x(n * L / 3), pts(n * L);
+    std::vector<uint8_t> flags(n);
+    for (size_t i = 0; i < n; i++) {
+        const char *p = &buf[i * (xb + 2)];
+        flags[i] = (uint8_t)((p[0] == '1' ? 2 : 0) | (p[xb + 1] == '1' ? 1 : 0));
+        std::memcpy(reinterpret_cast<char *>(x.data()) + i * xb, p + 1, xb);
+    }
+    check(group_traits<T>::group == 0 ? b200_decompress_g1(x.data(), flags.data(), n, wire_traits<T>::flavour(), pts.data(), nullptr)
+                                      : b200_decompress_g2(x.data(), flags.data(), n, wire_traits<T>::flavour(), pts.data(), nullptr),
+          "b200_decompress");
+    for (size_t i = 0; i < n; i++) v[i] = point_from_limbs<T>(pts.data() + i * L);
+}
+#endif  // BINARY_OUTPUT && point compression
 
 }  // namespace b200shim
 #endif  // B200_LIBFF_HPP_

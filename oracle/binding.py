@@ -269,6 +269,36 @@ class Checker:
             out[i] = self.msm("g1", bases[:m], w[start:start + m], chunks=1, variant=1)
         return out
 
+    # -- wire format: point compression ---------------------------------
+    def compress(self, group, pts, flavour=0):
+        """(x (n, 4|8), flags (n,) uint8).  ref: the reference's operator<< (flavour 0 -> alt_bn128, 2 -> bn128)."""
+        L = 12 if group == "g1" else 24
+        pts = _c(pts, L)
+        n = pts.shape[0]
+        x = np.zeros((n, L // 3), dtype=np.uint64)
+        flags = np.zeros(n, dtype=np.uint8)
+        fp = flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+        if self.kind == "ref":
+            assert flavour in (0, 2), "the reference build has alt_bn128 (flavour 0) and bn128 (flavour 2)"
+            self._call("compress_" + group, 0 if flavour == 0 else 1, _ptr(pts), ctypes.c_size_t(n), _ptr(x), fp)
+        else:
+            self._call("compress_" + group, _ptr(pts), ctypes.c_size_t(n), int(flavour), _ptr(x), fp)
+        return x, flags
+
+    def decompress(self, group, x, flags, flavour=0):
+        L = 12 if group == "g1" else 24
+        x = _c(x, L // 3)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        n = x.shape[0]
+        out = np.zeros((n, L), dtype=np.uint64)
+        fp = flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+        if self.kind == "ref":
+            assert flavour in (0, 2)
+            self._call("decompress_" + group, 0 if flavour == 0 else 1, _ptr(x), fp, ctypes.c_size_t(n), _ptr(out))
+        else:
+            self._call("decompress_" + group, _ptr(x), fp, ctypes.c_size_t(n), int(flavour), _ptr(out))
+        return out
+
     def one(self, group):
         L = 12 if group == "g1" else 24
         out = np.zeros(L, dtype=np.uint64)

@@ -676,6 +676,189 @@ int orc_fr_fft(uint64_t *a_, size_t log_n, int mode, const uint64_t *g_)
     return 0;
 }
 
+
+/* ------------------------------------------------------------------ */
+/* wire format: point compression               */
+/* operator<< / operator>> of alt_bn128_G1 (alt_bn128_g1.cpp:404-459),  */
+/* alt_bn128_G2 (alt_bn128_g2.cpp:414-475), bn128_G1 (bn128_g1.cpp:     */
+/* 344-463), bn128_G2 (bn128_g2.cpp:374-470), compression on.           */
+/* flavour 0: alt_bn128; 1: alt_bn128 -DMONTGOMERY_OUTPUT; 2: bn128.    */
+/* ------------------------------------------------------------------ */
+static void fq_pow_limbs(fq_t *o, const fq_t *a, const uint64_t *e, size_t nlimbs)
+{
+    fq_t r;
+    fq_set_one(&r);
+    for (size_t i = nlimbs * 64; i-- > 0;) {
+        fq_sqr(&r, &r);
+        if ((e[i / 64] >> (i % 64)) & 1) fq_mul(&r, &r, a);
+    }
+    *o = r;
+}
+static void fq2_pow_limbs(fq2_t *o, const fq2_t *a, const uint64_t *e, size_t nlimbs)
+{
+    fq2_t r;
+    fq2_set_one(&r);
+    for (size_t i = nlimbs * 64; i-- > 0;) {
+        fq2_sqr(&r, &r);
+        if ((e[i / 64] >> (i % 64)) & 1) fq2_mul(&r, &r, a);
+    }
+    *o = r;
+}
+/* Fp_model::sqrt (fp.tcc Tonelli-Shanks) for Fq: s = 1, t_minus_1_over_2 from alt_bn128_init.cpp:82-84;
+ * b = a^t is 1 for every square, so the loop body never runs and x = a * a^((t-1)/2) is returned */
+static void fq_sqrt(fq_t *o, const fq_t *a)
+{
+    /* 5472060717959818805561601436314318772174077789324455915672259473661306552145 */
+    static const uint64_t T12[4] = {0x4f082305b61f3f51ULL, 0x65e05aa45a1c72a3ULL, 0x6e14116da0605617ULL, 0x0c19139cb84c680aULL};
+    fq_t w;
+    fq_pow_limbs(&w, a, T12, 4);
+    fq_mul(o, a, &w);
+}
+/* Fp2_model::sqrt, fp2.tcc:146-200; s = 4, t_minus_1_over_2 and nqr_to_t from alt_bn128_init.cpp:92-98 */
+static void fq2_sqrt(fq2_t *o, const fq2_t *a)
+{
+    static const uint64_t T12[8] = {0x09daa2c5113aeb4dULL, 0xe5301039684f5608ULL, 0x425280c4e36cb656ULL, 0x682344f4abd09216ULL,
+                                    0x31376fd2e1a6359cULL, 0xe5805c2a88b1bab0ULL, 0xe2ccd37be01a4690ULL, 0x00492e25c3b1e5fcULL};
+    /* nqr_to_t = (5033503716262624267312492558379982687175200734934877598599011485707452665730,
+     *             314498342015008975724433667930697407966947188435857772134235984660852259084) */
+    static const uint64_t Z0[4] = {0x47cfbbedda71cf82ULL, 0x5398a41a4e1dc5d3ULL, 0x0dd3ecd4f3051527ULL, 0x0b20dcb5704e326aULL};
+    static const uint64_t Z1[4] = {0xab0f3a6ca462390cULL, 0xf05cfc50e9715370ULL, 0x2252522c29527d19ULL, 0x00b1ffefd8885bf2ULL};
+    fq2_t one, z, w, x, b;
+    fq2_set_one(&one);
+    fp_from_bigint(&z.c0, Z0, &FQ);
+    fp_from_bigint(&z.c1, Z1, &FQ);
+    size_t v = 4;
+    fq2_pow_limbs(&w, a, T12, 8);
+    fq2_mul(&x, a, &w);
+    fq2_mul(&b, &x, &w);
+    for (int guard = 0; guard < 8 && !fq2_eq(&b, &one); guard++) {
+        size_t m = 0;
+        fq2_t b2m = b;
+        while (!fq2_eq(&b2m, &one) && m < 8) {
+            fq2_sqr(&b2m, &b2m);
+            m += 1;
+        }
+        int j = (int)v - (int)m - 1;
+        w = z;
+        while (j > 0) {
+            fq2_sqr(&w, &w);
+            --j;
+        }
+        fq2_sqr(&z, &w);
+        fq2_mul(&b, &b, &z);
+        fq2_mul(&x, &x, &w);
+        v = m;
+    }
+    *o = x;
+}
+
+static void fq_to_wire(uint64_t o[4], const fq_t *x, int fl)
+{
+    if (fl == 0) fp_as_bigint(o, x->l, &FQ);
+    else memcpy(o, x->l, 32);
+}
+static void fq_from_wire(fq_t *o, const uint64_t x[4], int fl)
+{
+    if (fl == 0) fp_from_bigint(o, x, &FQ);
+    else memcpy(o->l, x, 32);
+}
+static unsigned fq_parity(const fq_t *y, int fl)
+{
+    uint64_t t[4];
+    if (fl == 2) return (unsigned)(y->l[0] & 1);
+    fp_as_bigint(t, y->l, &FQ);
+    return (unsigned)(t[0] & 1);
+}
+
+int orc_compress_g1(const uint64_t *pts, size_t n, int fl, uint64_t *x_out, uint8_t *flags)
+{
+    for (size_t i = 0; i < n; i++) {
+        g1_t p;
+        memcpy(&p, pts + 12 * i, sizeof p);
+        if (g1_is_zero(&p)) { /* to_affine_coordinates() turns a zero into (0, 1, 0) on both curves (alt_bn128_g1.cpp:60-67, bn128_g1.cpp:106-112) */
+            fq_t one = FQ.one, zero;
+            fq_set_zero(&zero);
+            fq_to_wire(x_out + 4 * i, &zero, fl);
+            flags[i] = (uint8_t)(2u | fq_parity(&one, fl));
+            continue;
+        }
+        g1_to_affine(&p);
+        fq_to_wire(x_out + 4 * i, &p.X, fl);
+        flags[i] = (uint8_t)fq_parity(&p.Y, fl);
+    }
+    return 0;
+}
+int orc_compress_g2(const uint64_t *pts, size_t n, int fl, uint64_t *x_out, uint8_t *flags)
+{
+    for (size_t i = 0; i < n; i++) {
+        g2_t p;
+        memcpy(&p, pts + 24 * i, sizeof p);
+        if (g2_is_zero(&p)) {
+            fq_t one = FQ.one, zero;
+            fq_set_zero(&zero);
+            fq_to_wire(x_out + 8 * i, &zero, fl);
+            fq_to_wire(x_out + 8 * i + 4, &zero, fl);
+            flags[i] = (uint8_t)(2u | fq_parity(&one, fl));
+            continue;
+        }
+        g2_to_affine(&p);
+        fq_to_wire(x_out + 8 * i, &p.X.c0, fl);
+        fq_to_wire(x_out + 8 * i + 4, &p.X.c1, fl);
+        flags[i] = (uint8_t)fq_parity(&p.Y.c0, fl);
+    }
+    return 0;
+}
+int orc_decompress_g1(const uint64_t *x, const uint8_t *flags, size_t n, int fl, uint64_t *pts_out)
+{
+    const uint64_t three[4] = {3, 0, 0, 0};
+    fq_t b;
+    fp_from_bigint(&b, three, &FQ); /* alt_bn128_coeff_b, alt_bn128_init.cpp:134 */
+    for (size_t i = 0; i < n; i++) {
+        g1_t g;
+        if (flags[i] & 2) {
+            g1_set_zero(&g);
+        } else {
+            fq_t x2, y2;
+            fq_from_wire(&g.X, x + 4 * i, fl);
+            fq_sqr(&x2, &g.X);
+            fq_mul(&y2, &x2, &g.X);
+            fq_add(&y2, &y2, &b);
+            fq_sqrt(&g.Y, &y2);
+            if (fq_parity(&g.Y, fl) != (unsigned)(flags[i] & 1)) fq_neg(&g.Y, &g.Y);
+            fq_set_one(&g.Z);
+        }
+        memcpy(pts_out + 12 * i, &g, sizeof g);
+    }
+    return 0;
+}
+int orc_decompress_g2(const uint64_t *x, const uint8_t *flags, size_t n, int fl, uint64_t *pts_out)
+{
+    /* alt_bn128_twist_coeff_b = 3 / (9 + u), alt_bn128_init.cpp:135-136 */
+    static const uint64_t B0[4] = {0x3267e6dc24a138e5ULL, 0xb5b4c5e559dbefa3ULL, 0x81be18991be06ac3ULL, 0x2b149d40ceb8aaaeULL};
+    static const uint64_t B1[4] = {0xe4a2bd0685c315d2ULL, 0xa74fa084e52d1852ULL, 0xcd2cafadeed8fdf4ULL, 0x009713b03af0fed4ULL};
+    fq2_t b;
+    fp_from_bigint(&b.c0, B0, &FQ);
+    fp_from_bigint(&b.c1, B1, &FQ);
+    for (size_t i = 0; i < n; i++) {
+        g2_t g;
+        if (flags[i] & 2) {
+            g2_set_zero(&g);
+        } else {
+            fq2_t x2, y2;
+            fq_from_wire(&g.X.c0, x + 8 * i, fl);
+            fq_from_wire(&g.X.c1, x + 8 * i + 4, fl);
+            fq2_sqr(&x2, &g.X);
+            fq2_mul(&y2, &x2, &g.X);
+            fq2_add(&y2, &y2, &b);
+            fq2_sqrt(&g.Y, &y2);
+            if (fq_parity(&g.Y.c0, fl) != (unsigned)(flags[i] & 1)) fq2_neg(&g.Y, &g.Y);
+            fq2_set_one(&g.Z);
+        }
+        memcpy(pts_out + 24 * i, &g, sizeof g);
+    }
+    return 0;
+}
+
 /* G1_one = (1,2,1): alt_bn128_init.cpp:148-150 ; G2_one: :209-213 */
 int orc_g1_one(uint64_t *out)
 {

@@ -76,6 +76,15 @@ int orc_fr_eval_mle(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *ou
 int orc_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
 int orc_fr_fft(uint64_t *a, size_t log_n, int mode, const uint64_t *g);
 
+/* wire format: the arithmetic of the reference's compressed operator<< / operator>>
+ * (alt_bn128_g1.cpp:404-459, alt_bn128_g2.cpp:414-475, bn128_g1.cpp:344-463, bn128_g2.cpp:374-470).
+ * flavour 0 alt_bn128, 1 alt_bn128 -DMONTGOMERY_OUTPUT, 2 bn128; flags[i]: bit 0 = Y bit, bit 1 = is_zero.
+ * ref_* (oracle/ref_wrap.cpp) runs the reference's own stream operators: curve 0 = flavour 0, curve 1 = flavour 2. */
+int orc_compress_g1(const uint64_t *pts, size_t n, int flavour, uint64_t *x_out, uint8_t *flags);
+int orc_compress_g2(const uint64_t *pts, size_t n, int flavour, uint64_t *x_out, uint8_t *flags);
+int orc_decompress_g1(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out);
+int orc_decompress_g2(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out);
+
 int orc_g1_one(uint64_t *out);
 int orc_g2_one(uint64_t *out);
 

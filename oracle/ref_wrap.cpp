@@ -16,6 +16,8 @@
 // G1 = X|Y|Z (12 limbs), G2 = X.c0|X.c1|Y.c0|Y.c1|Z.c0|Z.c1 (24 limbs).
 #include <cstdint>
 #include <cstring>
+#include <sstream>
+#include <string>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -413,3 +415,79 @@ int ref_g2_zero(int curve, uint64_t *out)
 }
 
 } // extern "C"
+
+// ---- wire format: the reference's own operator<< / operator>> with point compression,
+// through a string stream.  With -DBINARY_OUTPUT (how this library is built) a point is
+//   '0'|'1' (is_zero)  |  X raw bytes (32 for G1, 64 for G2)  |  '0'|'1' (Y bit)
+// alt_bn128: X = as_bigint (no -DMONTGOMERY_OUTPUT here) -> flavour 0 of include/b200_msm.h; bn128: flavour 2.
+template <typename G>
+int compress_impl(const uint64_t *pts, size_t n, uint64_t *x_out, uint8_t *flags)
+{
+    const size_t L = limbs_of<G>(), xb = L / 3 * 8;
+    for (size_t i = 0; i < n; i++) {
+        G g;
+        load(g, pts + i * L);
+        std::ostringstream os;
+        os << g;
+        const std::string s = os.str();
+        if (s.size() != xb + 2) return 3;
+        memcpy((char *)x_out + i * xb, s.data() + 1, xb);
+        flags[i] = (uint8_t)((s[0] == '1' ? 2 : 0) | (s[xb + 1] == '1' ? 1 : 0));
+    }
+    return 0;
+}
+template <typename G>
+int decompress_impl(const uint64_t *x, const uint8_t *flags, size_t n, uint64_t *pts_out)
+{
+    const size_t L = limbs_of<G>(), xb = L / 3 * 8;
+    for (size_t i = 0; i < n; i++) {
+        std::string s(xb + 2, '0');
+        s[0] = (flags[i] & 2) ? '1' : '0';
+        memcpy(&s[1], (const char *)x + i * xb, xb);
+        s[xb + 1] = (flags[i] & 1) ? '1' : '0';
+        std::istringstream is(s);
+        G g;
+        is >> g;
+        store(pts_out + i * L, g);
+    }
+    return 0;
+}
+
+extern "C" {
+int ref_compress_g1(int curve, const uint64_t *pts, size_t n, uint64_t *x_out, uint8_t *flags)
+{
+    ref_init();
+    if (curve == 0) return compress_impl<alt_bn128_G1>(pts, n, x_out, flags);
+#ifdef REF_WITH_BN128
+    if (curve == 1) return compress_impl<bn128_G1>(pts, n, x_out, flags);
+#endif
+    return 2;
+}
+int ref_compress_g2(int curve, const uint64_t *pts, size_t n, uint64_t *x_out, uint8_t *flags)
+{
+    ref_init();
+    if (curve == 0) return compress_impl<alt_bn128_G2>(pts, n, x_out, flags);
+#ifdef REF_WITH_BN128
+    if (curve == 1) return compress_impl<bn128_G2>(pts, n, x_out, flags);
+#endif
+    return 2;
+}
+int ref_decompress_g1(int curve, const uint64_t *x, const uint8_t *flags, size_t n, uint64_t *pts_out)
+{
+    ref_init();
+    if (curve == 0) return decompress_impl<alt_bn128_G1>(x, flags, n, pts_out);
+#ifdef REF_WITH_BN128
+    if (curve == 1) return decompress_impl<bn128_G1>(x, flags, n, pts_out);
+#endif
+    return 2;
+}
+int ref_decompress_g2(int curve, const uint64_t *x, const uint8_t *flags, size_t n, uint64_t *pts_out)
+{
+    ref_init();
+    if (curve == 0) return decompress_impl<alt_bn128_G2>(x, flags, n, pts_out);
+#ifdef REF_WITH_BN128
+    if (curve == 1) return decompress_impl<bn128_G2>(x, flags, n, pts_out);
+#endif
+    return 2;
+}
+}  // extern "C"
