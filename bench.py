@@ -317,13 +317,14 @@ def main():
     sampler = ClockSampler(local_rank)
     time.sleep(0.25)
     t_start = time.perf_counter()
-    res_ms, acc_ms, fin_us = [], [], []
+    res_ms, acc_ms, fin_us, sort_ms = [], [], [], []
     result = None
     for _ in range(args.steps):
         result, ms, st = step_resident()
         res_ms.append(ms)
         acc_ms.append(st["accumulate_ms"])
         fin_us.append(st["host_finalize_us"])
+        sort_ms.append(st["sort_ms"])
     barrier()
     t_end = time.perf_counter()
     clocks = sampler.stop(t_start, t_end)
@@ -379,6 +380,12 @@ def main():
                         "imad_per_modmul": 136, "modmul_per_mixed_add_executed": MODMUL_ACTUAL},
         "modmul_per_s": entries * MODMUL_ACTUAL / (acc * 1e-3), "modmul_per_s_peak_measured": modmul_peak,
         "imad32_peak": imad32_peak / 1e12,
+        # digit sort (count + scans + scatter + task lists): scalars read once, W digits written and read back,
+        # W bucket-ordered entries written; north star: "HBM GB/s for the sort and gather phases"
+        "hbm_sort": {"bytes_per_step": n * 32.0 + 3.0 * 4.0 * stats["num_windows"] * n, "ms": float(np.mean(sort_ms)),
+                     "achieved_gbs": (n * 32.0 + 12.0 * stats["num_windows"] * n) / (float(np.mean(sort_ms)) * 1e-3) / 1e9,
+                     "peak_gbs": hbm_gbs, "frac": (n * 32.0 + 12.0 * stats["num_windows"] * n) / (float(np.mean(sort_ms)) * 1e-3) / 1e9 / hbm_gbs,
+                     "note": "atomics-bound (W n histogram + W n cursor updates), not bandwidth-bound"},
         "hbm": {"gather_bytes_per_launch": gather_bytes, "achieved_gbs": gather_bytes / (acc * 1e-3) / 1e9,
                 "peak_gbs": hbm_gbs, "peak_source": hbm_src, "frac": gather_bytes / (acc * 1e-3) / 1e9 / hbm_gbs},
     }

@@ -220,6 +220,7 @@ typedef struct {
     uint64_t num_entries;      /* bucket entries = mixed additions done by k_accumulate (device 0) */
     double accumulate_ms;      /* CUDA-event time of k_accumulate on device 0 */
     double device_ms;          /* CUDA-event time of the whole enqueued pipeline on device 0 */
+    double sort_ms;            /* CUDA-event time from the start of the pipeline to the start of k_accumulate: the digit sort */
 } b200_stats_t;
 int b200_last_stats(b200_stats_t *out);
 /* Overrides for tuning / tests: window bits c (0 = auto), chunk length L (0 = auto). */

@@ -50,7 +50,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("n", ctypes.c_uint64), ("window_bits", ctypes.c_uint32), ("num_windows", ctypes.c_uint32),
                 ("chunk_len", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32), ("num_tasks", ctypes.c_uint64),
                 ("host_finalize_us", ctypes.c_double), ("h2d_bytes", ctypes.c_double), ("d2h_bytes", ctypes.c_double),
-                ("num_entries", ctypes.c_uint64), ("accumulate_ms", ctypes.c_double), ("device_ms", ctypes.c_double)]
+                ("num_entries", ctypes.c_uint64), ("accumulate_ms", ctypes.c_double), ("device_ms", ctypes.c_double),
+                ("sort_ms", ctypes.c_double)]
 
 
 _lib = None

@@ -127,6 +127,7 @@ inline void fill_stats(const Device &D, size_t n, const MsmGeom &g, const uint32
     float ms = 0;
     if (cudaEventElapsedTime(&ms, D.ev[2], D.ev[3]) == cudaSuccess) g_stats.accumulate_ms = ms;
     if (cudaEventElapsedTime(&ms, D.ev[0], D.ev[1]) == cudaSuccess) g_stats.device_ms = ms;
+    if (cudaEventElapsedTime(&ms, D.ev[0], D.ev[2]) == cudaSuccess) g_stats.sort_ms = ms;
 }
 
 // ------------------------------------------------------------------------------

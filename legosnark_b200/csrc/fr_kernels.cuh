@@ -166,8 +166,12 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
                                                                     const Fr *__restrict__ tw, const Fr *__restrict__ pre,
                                                                     const Fr *__restrict__ post, const Fr *__restrict__ post_scalar)
 {
-    extern __shared__ uint32_t sm[];  // 8 limb planes of E words: sm[l * E + e]
+    // 8 limb planes; element e sits at word e + (e >> 5) of its plane (one pad word per 32) so that the stride-4 and
+    // stride-2 accesses of the first radix-4 trips fall on distinct banks
+    extern __shared__ uint32_t sm[];
     const uint32_t E = 1u << (P.k + P.t);
+    const uint32_t EP = E + (E >> 5);
+#define FFT_AT(i, e) sm[(i) * EP + (e) + ((e) >> 5)]
     const uint32_t tmask = (1u << P.t) - 1u;
     // block -> (hi, lo0): idx = hi 2^(s0+k) + mid 2^s0 + lo0 + l
     size_t hi, lo0;
@@ -192,7 +196,7 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
             v = src[idx];
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++) sm[i * E + e] = v.l[i];
+        for (int i = 0; i < 8; i++) FFT_AT(i, e) = v.l[i];
     }
     __syncthreads();
     // two stages per trip through shared memory (radix 4 in registers): the thread owns the four
@@ -212,10 +216,10 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
             Fr a00, a01, a10, a11;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                a00.l[i] = sm[i * E + e00];
-                a01.l[i] = sm[i * E + e01];
-                a10.l[i] = sm[i * E + e10];
-                a11.l[i] = sm[i * E + e11];
+                a00.l[i] = FFT_AT(i, e00);
+                a01.l[i] = FFT_AT(i, e01);
+                a10.l[i] = FFT_AT(i, e10);
+                a11.l[i] = FFT_AT(i, e11);
             }
             // stage q
             if (ja) {
@@ -240,10 +244,10 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
             a01 = Fr::add(a01, t);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                sm[i * E + e00] = a00.l[i];
-                sm[i * E + e01] = a01.l[i];
-                sm[i * E + e10] = a10.l[i];
-                sm[i * E + e11] = a11.l[i];
+                FFT_AT(i, e00) = a00.l[i];
+                FFT_AT(i, e01) = a01.l[i];
+                FFT_AT(i, e10) = a10.l[i];
+                FFT_AT(i, e11) = a11.l[i];
             }
         }
         __syncthreads();
@@ -260,15 +264,15 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
             Fr a, b;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                a.l[i] = sm[i * E + e0];
-                b.l[i] = sm[i * E + e1];
+                a.l[i] = FFT_AT(i, e0);
+                b.l[i] = FFT_AT(i, e1);
             }
             const Fr tt = j ? Fr::mul(tw[j << tw_shift], b) : b;
             const Fr lo = Fr::add(a, tt), hi2 = Fr::sub(a, tt);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                sm[i * E + e0] = lo.l[i];
-                sm[i * E + e1] = hi2.l[i];
+                FFT_AT(i, e0) = lo.l[i];
+                FFT_AT(i, e1) = hi2.l[i];
             }
         }
         __syncthreads();
@@ -279,11 +283,12 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
         const size_t idx = base + ((size_t)mid << P.s0) + l;
         Fr v;
 #pragma unroll
-        for (int i = 0; i < 8; i++) v.l[i] = sm[i * E + e];
+        for (int i = 0; i < 8; i++) v.l[i] = FFT_AT(i, e);
         if (last && post) v = Fr::mul(v, post[idx]);
         else if (last && post_scalar) v = Fr::mul(v, *post_scalar);
         dst[idx] = v;
     }
+#undef FFT_AT
 }
 
 }  // namespace b200

@@ -810,23 +810,21 @@ __global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits(const XYZZ<F> *__r
     }
     __syncthreads();
     if (ticket != nout - 1) return;
-    // last block of window k: every block's result is visible
+    // last block of window k: every block's result is visible; the whole block sums them
     __threadfence();
-    if (threadIdx.x < 32) {
-        XYZZ<F> v = XYZZ<F>::inf();
-        for (uint32_t o = threadIdx.x; o < nout; o += 32) {
-            const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(&job_out[(size_t)k * nout + o]);
-            XYZZ<F> q;
-            uint32_t *d = reinterpret_cast<uint32_t *>(&q);
+    XYZZ<F> v = XYZZ<F>::inf();
+    for (uint32_t o = threadIdx.x; o < nout; o += RED2_THREADS) {
+        const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(&job_out[(size_t)k * nout + o]);
+        XYZZ<F> q;
+        uint32_t *d = reinterpret_cast<uint32_t *>(&q);
 #pragma unroll
-            for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = p[i];
-            xyzz_add_cold(&v, &q);
-        }
-        v = warp_sum_point(v);
-        if (threadIdx.x == 0) {
-            window_sums[k] = v;
-            done[k] = 0;  // ready for the next call
-        }
+        for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = p[i];
+        xyzz_add_cold(&v, &q);
+    }
+    v = block_sum_point(v, sm);  // sm is free again: all threads passed the barrier above
+    if (threadIdx.x == 0) {
+        window_sums[k] = v;
+        done[k] = 0;  // ready for the next call
     }
 }
 
