@@ -212,7 +212,7 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
             const Fr *src = pi == 0 ? data : work;
             Fr *dst = (last && pi > 0) ? data : work;
             const uint32_t E = 1u << (P.k + P.t);
-            LAUNCH(D, k_fr_fft_pass, (uint32_t)(n / E), FFT_THREADS, (size_t)8 * (E + (E >> 5)) * 4, st, src, dst, P, tw, pi == 0 ? pre : (const Fr *)nullptr,
+            LAUNCH(D, k_fr_fft_pass, (uint32_t)(n / E), FFT_THREADS, (size_t)8 * E * 4, st, src, dst, P, tw, pi == 0 ? pre : (const Fr *)nullptr,
                    last ? post : (const Fr *)nullptr, last ? post_scalar : (const Fr *)nullptr);
         }
         if (plan.size() == 1) CK(cudaMemcpyAsync(data, work, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));

@@ -166,12 +166,11 @@ static __global__ void __launch_bounds__(FFT_THREADS) k_fr_fft_pass(const Fr *__
                                                                     const Fr *__restrict__ tw, const Fr *__restrict__ pre,
                                                                     const Fr *__restrict__ post, const Fr *__restrict__ post_scalar)
 {
-    // 8 limb planes; element e sits at word e + (e >> 5) of its plane (one pad word per 32) so that the stride-4 and
-    // stride-2 accesses of the first radix-4 trips fall on distinct banks
+    // 8 limb planes of E words (a one-word-per-32 padding of the planes was measured: no change, the passes are
+    // bound by the multiply-add pipe, not by shared-memory wavefronts)
     extern __shared__ uint32_t sm[];
     const uint32_t E = 1u << (P.k + P.t);
-    const uint32_t EP = E + (E >> 5);
-#define FFT_AT(i, e) sm[(i) * EP + (e) + ((e) >> 5)]
+#define FFT_AT(i, e) sm[(i) * E + (e)]
     const uint32_t tmask = (1u << P.t) - 1u;
     // block -> (hi, lo0): idx = hi 2^(s0+k) + mid 2^s0 + lo0 + l
     size_t hi, lo0;
