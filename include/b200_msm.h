@@ -226,6 +226,7 @@ int b200_last_stats(b200_stats_t *out);
 /* Overrides for tuning / tests: window bits c (0 = auto), chunk length L (0 = auto). */
 int b200_set_tuning(int window_bits, int chunk_len);
 /* More knobs for sweeps: "reduce_log_segment" (-1 = model), "reduce_split" (0 = auto),
+ * "host_horner" (0: a precomputed key's one-window reduction is weighted and summed on the device too),
  * "ones_filter" (0: scalars equal to one go through the bucket sort instead of the direct sum),
  * "use_precomputed" (0: ignore a key's precomputed levels; 1: where the cost model prefers them; 2: always). */
 int b200_set_tuning_ex(const char *key, int value);

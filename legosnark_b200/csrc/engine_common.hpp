@@ -161,7 +161,7 @@ extern std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
 extern std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
-extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre, g_tune_ones;
+extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre, g_tune_ones, g_tune_host_horner;
 // set while the second MSM of a knowledge-commitment pair runs: every device still holds the
 // scalars of its shard in D.scalars from the first one, so the host-buffer paths skip that upload
 extern bool g_scalars_resident;

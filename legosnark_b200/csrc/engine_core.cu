@@ -29,7 +29,7 @@ std::map<uint64_t, std::unique_ptr<PinnedBases>> g_pinned;
 std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
-int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1;
+int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1, g_tune_host_horner = 1;
 bool g_scalars_resident = false;
 
 static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal
@@ -454,6 +454,7 @@ int b200_set_tuning_ex(const char *key, int value)
     if (k == "reduce_log_segment") g_tune_logS = value;       // -1 = model
     else if (k == "reduce_split") g_tune_split = value;       // 0 = auto
     else if (k == "use_precomputed") g_tune_pre = value;      // 0: ignore precomputed levels of a key
+    else if (k == "host_horner") g_tune_host_horner = value;  // 0: the device also weights and sums the per-job results of a one-window reduction
     else if (k == "ones_filter") g_tune_ones = value;         // 0: scalars equal to one go through the sort like any other
     else return fail(B200_ERR_ARG, "unknown tuning key %s", key);
     return B200_OK;

@@ -52,6 +52,7 @@ inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride
     g.pre_stride = pre_c ? pre_stride : 0;
     g.pre_off = pre_c ? pre_off : 0;
     g.ones = g_tune_ones ? 1 : 0;
+    g.red_jobs = g.red_logS = 0;
     g.NB = g.Wb * g.B;
     if (g_tune_L > 0) {
         g.L = (uint32_t)std::min(std::max(g_tune_L, 1), 1023);
@@ -188,6 +189,11 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     P.split = RED2_SPLIT;
     if (g.Wb == 1) P.split = std::min<uint32_t>(32, std::max<uint32_t>(2, cdiv((size_t)D.sms * 2, P.njobs + 1)));
     if (g_tune_split > 0) P.split = (uint32_t)std::min(g_tune_split, 64);
+    if (g.Wb == 1 && !dense && g_tune_host_horner) {  // one window: per-job sums to the host (MsmGeom::red_jobs)
+        P.g.red_jobs = P.njobs;
+        P.g.red_logS = P.logS;
+    }
+    const uint32_t nres = result_points(P.g);
 
     D.cnt.ensure((size_t)g.NB * 4);
     D.off.ensure((size_t)g.NB * 4);
@@ -208,12 +214,12 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.split.ensure(std::min<size_t>(g.NB, P.max_tasks) * 4 + 4);
     D.big.ensure(std::min<size_t>(g.NB, P.max_tasks / BIG_TASKS + 1) * 4 + 4);
     if (dense) D.bucket_sum.ensure((size_t)g.NB * sizeof(XYZZ<F>));
-    if (D.done.cap < (size_t)g.Wb * 4) {
+    if (D.done.cap < (size_t)std::max<uint32_t>(g.Wb, 64) * 4) {
         D.done.ensure(1024 * 4);
         CK(cudaMemsetAsync(D.done.p, 0, D.done.cap, st));  // k_reduce_bits leaves the counters at zero
     }
-    D.window_sums.ensure((size_t)g.Wb * sizeof(XYZZ<F>));
-    D.ensure_pinned((size_t)(g.Wb + 2) * sizeof(XYZZ<F>) + 64);
+    D.window_sums.ensure((size_t)nres * sizeof(XYZZ<F>));
+    D.ensure_pinned((size_t)(nres + 2) * sizeof(XYZZ<F>) + 64);
     if (g.ones) {
         D.ones_idx.ensure(chunk_max * 4);
         D.ones_part.ensure((size_t)D.sms * 2 * sizeof(XYZZ<F>));
@@ -289,12 +295,13 @@ void enqueue_reduce(Device &D, cudaStream_t st, const MsmPlan &P, bool dense)
     XYZZ<F> *seg_run = D.seg_run.as<XYZZ<F>>(), *seg_acc = D.seg_acc.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
     LAUNCH(D, (k_reduce_segments<F>), cdiv(P.nseg, RED_THREADS), RED_THREADS, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(),
            D.partial.as<XYZZ<F>>(), dense ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr, g, P.logS, seg_run, seg_acc);
+    const uint32_t nres = result_points(g);
     LAUNCH(D, (k_reduce_bits<F>), dim3((P.njobs + 1) * P.split, g.Wb), RED2_THREADS, 0, st, seg_run, seg_acc, P.M, P.logS,
-           P.split, D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
-    CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)g.Wb * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)g.Wb * sizeof(XYZZ<F>), D.totals.p, 8, cudaMemcpyDeviceToHost, st));
+           P.split, g.red_jobs ? 1u : 0u, D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
+    CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)nres * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)nres * sizeof(XYZZ<F>), D.totals.p, 8, cudaMemcpyDeviceToHost, st));
     if (g.ones)
-        CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)(g.Wb + 1) * sizeof(XYZZ<F>), D.ones_sum.p, sizeof(XYZZ<F>),
+        CK(cudaMemcpyAsync((char *)D.h_pinned + (size_t)(nres + 1) * sizeof(XYZZ<F>), D.ones_sum.p, sizeof(XYZZ<F>),
                            cudaMemcpyDeviceToHost, st));
 }
 
@@ -377,13 +384,24 @@ host::HJac<typename HostOf<F>::type> finalize_windows(const Device &D, const Msm
     static_assert(sizeof(HX) == sizeof(XYZZ<F>), "host/device XYZZ images must match");
     const HX *ws = reinterpret_cast<const HX *>(D.h_pinned);
     J acc = J::inf();
-    for (int k = (int)g.Wb - 1; k >= 0; k--) {
+    if (g.red_jobs) {
+        // one window, per-job sums: ws[0] = S_0 = sum_s acc_s, ws[1 + b] = T_b; R = S_0 + 2^logS sum_b 2^b T_b (Horner)
+        for (int b = (int)g.red_jobs - 2; b >= 0; b--) {
+            if (!acc.is_inf()) acc = host::jac_dbl(acc);
+            acc = host::jac_add(acc, host::jac_from_xyzz(ws[1 + b].x, ws[1 + b].y, ws[1 + b].zz, ws[1 + b].zzz));
+        }
         if (!acc.is_inf())
-            for (uint32_t i = 0; i < g.c; i++) acc = host::jac_dbl(acc);
-        acc = host::jac_add(acc, host::jac_from_xyzz(ws[k].x, ws[k].y, ws[k].zz, ws[k].zzz));
+            for (uint32_t i = 0; i < g.red_logS; i++) acc = host::jac_dbl(acc);
+        acc = host::jac_add(acc, host::jac_from_xyzz(ws[0].x, ws[0].y, ws[0].zz, ws[0].zzz));
+    } else {
+        for (int k = (int)g.Wb - 1; k >= 0; k--) {
+            if (!acc.is_inf())
+                for (uint32_t i = 0; i < g.c; i++) acc = host::jac_dbl(acc);
+            acc = host::jac_add(acc, host::jac_from_xyzz(ws[k].x, ws[k].y, ws[k].zz, ws[k].zzz));
+        }
     }
     if (g.ones) {  // the bases with scalar one, summed by k_sum_ones (weight 1)
-        const HX &o = ws[g.Wb + 1];
+        const HX &o = ws[result_points(g) + 1];
         acc = host::jac_add(acc, host::jac_from_xyzz(o.x, o.y, o.zz, o.zzz));
     }
     return acc;
@@ -415,6 +433,7 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         g.NB = g.W * g.B;
         g.Wb = g.W;
         g.pre_stride = g.pre_off = g.ones = 0;
+        g.red_jobs = g.red_logS = 0;
         g.L = 0;
         D.scalars.ensure(n * sizeof(Fr));
         D.bases_jac.ensure(n * sizeof(Jacobian<F>));
@@ -474,12 +493,12 @@ int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t 
             partials[si] = finalize_windows<F>(g_devs[si], geoms[si]);
             total = host::jac_add(total, partials[si]);
             h2d += (double)ranges[si].second * ((g_scalars_resident ? 0 : sizeof(Fr)) + sizeof(Jacobian<F>));
-            d2h += (double)geoms[si].Wb * sizeof(XYZZ<F>) + 8;
+            d2h += (double)result_points(geoms[si]) * sizeof(XYZZ<F>) + 8;
         }
         write_point<HF>(out, total);
         const auto t1 = std::chrono::steady_clock::now();
         const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)g_devs[0].h_pinned +
-                                                                 (size_t)geoms[0].Wb * sizeof(XYZZ<F>));
+                                                                 (size_t)result_points(geoms[0]) * sizeof(XYZZ<F>));
         fill_stats(g_devs[0], ranges[0].second, geoms[0], tot, std::chrono::duration<double, std::micro>(t1 - t0).count(), h2d, d2h);
         return B200_OK;
     } catch (const CudaError &e) {
@@ -622,6 +641,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
                 g.B = SMALL_NBK;
                 g.NB = g.W * g.B;
                 g.pre_stride = g.pre_off = g.ones = 0;
+                g.red_jobs = g.red_logS = 0;
                 g.L = 0;
                 D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
                 D.totals.ensure(32);
@@ -655,12 +675,12 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
         double d2h = 0;
         for (size_t pi = 0; pi < pieces.size(); pi++) {
             total = host::jac_add(total, finalize_windows<F>(g_devs[pb.shards[pieces[pi].shard].dev], geoms[pi]));
-            d2h += (double)geoms[pi].Wb * sizeof(XYZZ<F>) + 8;
+            d2h += (double)result_points(geoms[pi]) * sizeof(XYZZ<F>) + 8;
         }
         write_point<HF>(out, total);
         const auto t1 = std::chrono::steady_clock::now();
         const Device &D0 = g_devs[pb.shards[pieces[0].shard].dev];
-        const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)D0.h_pinned + (size_t)geoms[0].Wb * sizeof(XYZZ<F>));
+        const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)D0.h_pinned + (size_t)result_points(geoms[0]) * sizeof(XYZZ<F>));
         fill_stats(D0, pieces[0].cnt, geoms[0], tot, std::chrono::duration<double, std::micro>(t1 - t0).count(),
                    d_scalars ? 0.0 : (double)n * sizeof(Fr), d2h);
         return B200_OK;

@@ -47,7 +47,12 @@ struct MsmGeom {
     uint32_t pre_stride;  // points per level of the precomputed table (0: plain key)
     uint32_t pre_off;     // first point of this MSM inside its level
     uint32_t ones;        // 1: scalars equal to one were set aside by k_digit_count and summed by k_sum_ones
+    // window reduction of a precomputed key (one window): the device returns the per-job sums S_0, T_0 .. T_{jobs-2}
+    // and the host forms S_0 + 2^logS sum_b 2^b T_b (a few dozen cheap host operations instead of a serial chain
+    // of doublings and a second combine on a lone warp).  red_jobs == 0: the device returns the window sums.
+    uint32_t red_jobs, red_logS;
 };
+__host__ __device__ __forceinline__ uint32_t result_points(const MsmGeom &g) { return g.red_jobs ? g.red_jobs : g.Wb; }
 __host__ __device__ __forceinline__ uint32_t bucket_base(const MsmGeom &g, uint32_t k) { return g.pre_stride ? 0u : k * g.B; }
 
 // ------------------------------------------------------------------------------
@@ -780,8 +785,9 @@ constexpr int RED2_SPLIT = 2;  // blocks per job with W windows of buckets; a pr
 
 template <class F>
 __global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits(const XYZZ<F> *__restrict__ seg_run, const XYZZ<F> *__restrict__ seg_acc,
-                                                               uint32_t M, uint32_t logS, uint32_t split, XYZZ<F> *__restrict__ job_out,
-                                                               uint32_t *__restrict__ done, XYZZ<F> *__restrict__ window_sums)
+                                                               uint32_t M, uint32_t logS, uint32_t split, uint32_t per_job,
+                                                               XYZZ<F> *__restrict__ job_out, uint32_t *__restrict__ done,
+                                                               XYZZ<F> *__restrict__ window_sums)
 {
     __shared__ XYZZ<F> sm[RED2_THREADS / 32];
     __shared__ uint32_t ticket;
@@ -802,13 +808,32 @@ __global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits(const XYZZ<F> *__r
     }
     acc = block_sum_point(acc, sm);
     if (threadIdx.x == 0) {
-        if (job > 0)
+        if (job > 0 && !per_job)
             for (uint32_t i = 0; i < bit + logS; i++) xyzz_dbl_cold(&acc);
         job_out[(size_t)k * nout + blockIdx.x] = acc;
         __threadfence();
-        ticket = atomicAdd(&done[k], 1u);
+        ticket = atomicAdd(&done[per_job ? job : k], 1u);
     }
     __syncthreads();
+    if (per_job) {
+        // one window (precomputed key): the last block of each job sums that job's partials; weights on the host
+        if (ticket != nparts - 1) return;
+        __threadfence();
+        const uint32_t first = job == 0 ? 0 : (job + 1) * split;
+        XYZZ<F> v = XYZZ<F>::inf();
+        if (threadIdx.x < nparts) {
+            const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(&job_out[first + threadIdx.x]);
+            uint32_t *d = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = p[i];
+        }
+        v = block_sum_point(v, sm);
+        if (threadIdx.x == 0) {
+            window_sums[job] = v;
+            done[job] = 0;
+        }
+        return;
+    }
     if (ticket != nout - 1) return;
     // last block of window k: every block's result is visible; the whole block sums them
     __threadfence();

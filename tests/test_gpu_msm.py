@@ -127,6 +127,11 @@ def test_precomputed_key(engine, orc, golden, grp, n):
                     want = orc.msm(grp, P[off:off + m], s, chunks=orc.max_threads())
                     got = key.multi_exp(s, offset=off)
                     assert (got == want).all(), (grp, c, m, off)
+                    engine.set_tuning_ex("host_horner", 0)  # the device weights and sums the per-job results itself
+                    try:
+                        assert (key.multi_exp(s, offset=off) == want).all(), (grp, c, m, off, "device horner")
+                    finally:
+                        engine.set_tuning_ex("host_horner", 1)
             if c:
                 st = engine.last_stats()
                 assert st["window_bits"] == c, "precomputed path was not taken"
