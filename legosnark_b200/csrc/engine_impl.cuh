@@ -62,8 +62,10 @@ inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride
         while (L < 2.0 * avg && L < 512) L <<= 1;
         // k_accumulate runs one thread per task: keep several waves of tasks in flight even when
         // few buckets hold many entries each (a precomputed key with a small window)
-        const double cap = (double)n * g.W / (148.0 * 512.0 * 6.0);
-        while (pre_c && L > 32 && L > cap) L >>= 1;
+        // ... unless the buckets themselves are already that many tasks (one task per bucket needs no combine)
+        const double want_tasks = 148.0 * 512.0 * 6.0;
+        const double cap = (double)n * g.W / want_tasks;
+        while (pre_c && (double)g.NB < want_tasks && L > 32 && L > cap) L >>= 1;
         g.L = L;
     }
     return g;
@@ -185,9 +187,9 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     while ((1u << (P.njobs - 1)) < P.M) P.njobs++;  // job 0 + one job per bit of the segment index
     P.nseg = (size_t)g.Wb * P.M;
     // blocks per job of stage 2: W windows already fill the machine with 2; a lone window
-    // (precomputed key) spreads its jobs over ~2 blocks per SM
+    // (precomputed key) spreads each job over 8-16 blocks
     P.split = RED2_SPLIT;
-    if (g.Wb == 1) P.split = std::min<uint32_t>(32, std::max<uint32_t>(2, cdiv((size_t)D.sms * 2, P.njobs + 1)));
+    if (g.Wb == 1) P.split = P.M <= (1u << 14) ? 8 : 16;  // swept: profiles/r15b_reduce_sweep_*.jsonl
     if (g_tune_split > 0) P.split = (uint32_t)std::min(g_tune_split, 64);
     if (g.Wb == 1 && !dense && g_tune_host_horner) {  // one window: per-job sums to the host (MsmGeom::red_jobs)
         P.g.red_jobs = P.njobs;
