@@ -15,6 +15,9 @@ import numpy as np
 from . import shard_range, sum_partials  # noqa: F401  (re-exported)
 
 
+_bufs = {}  # (limbs, device) -> (pinned in, device in, device out, pinned out): allocated once, the gather runs every step
+
+
 def gather_partials(partial: np.ndarray, device=None) -> np.ndarray | None:
     """all_gather each rank's partial point; returns (world, limbs) uint64 on every rank."""
     import torch
@@ -23,13 +26,24 @@ def gather_partials(partial: np.ndarray, device=None) -> np.ndarray | None:
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return np.asarray(partial, dtype=np.uint64).reshape(1, -1)
     world = dist.get_world_size()
-    t = torch.from_numpy(np.ascontiguousarray(partial, dtype=np.uint64).view(np.int64).copy())
+    flat = np.ascontiguousarray(partial, dtype=np.uint64).reshape(-1)
+    if dist.get_backend() == "nccl" and device is not None:
+        key = (flat.shape[0], str(device))
+        if key not in _bufs:
+            _bufs[key] = (torch.empty(flat.shape[0], dtype=torch.int64).pin_memory(),
+                          torch.empty(flat.shape[0], dtype=torch.int64, device=device),
+                          torch.empty((world, flat.shape[0]), dtype=torch.int64, device=device),
+                          torch.empty((world, flat.shape[0]), dtype=torch.int64).pin_memory())
+        h_in, d_in, d_out, h_out = _bufs[key]
+        h_in.numpy()[:] = flat.view(np.int64)
+        d_in.copy_(h_in, non_blocking=True)
+        dist.all_gather_into_tensor(d_out, d_in)  # one collective of a few hundred bytes (transport, not a data-path collective)
+        h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        return h_out.numpy().view(np.uint64).copy()
+    t = torch.from_numpy(flat.view(np.int64).copy())
     if device is not None:
         t = t.to(device)
-    if dist.get_backend() == "nccl":
-        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t)  # one collective, one device-to-host read
-        return out.cpu().numpy().view(np.uint64).reshape(world, -1)
     outs = [torch.empty_like(t) for _ in range(world)]  # gloo (CPU tests): list form
     dist.all_gather(outs, t)
     return np.stack([o.cpu().numpy().view(np.uint64) for o in outs])
