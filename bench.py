@@ -250,10 +250,11 @@ def main():
             dist.barrier()
 
     def align():
-        """The L2 flush is test hygiene, not part of a step: line the ranks up after it so that the gather of the
+        """The L2 flush is test hygiene, not part of a step: wait for it (it would otherwise run next to the first
+        kernels of the step and take their bandwidth) and line the ranks up after it, so that the gather of the
         partials inside the timed region does not wait for a peer that is still flushing."""
+        torch.cuda.synchronize()  # the flush runs on torch's stream, the engine on its own: do not let them overlap
         if world > 1:
-            torch.cuda.synchronize()
             dist.barrier()
 
     def step_resident():
@@ -435,7 +436,7 @@ def main():
                        "key": ("plain affine key" if plain is None else
                                f"precomputed key: window multiples 2^(c k) P_i resident in HBM ({stats['num_windows']} x 64 B per base), "
                                "all windows share one bucket set; one-off cost in plain_key.key_precompute_ms_one_off"),
-                       "l2": "flushed between timed iterations (512 MiB write)", "sharding": f"index range x{world}, host sum of partials"},
+                       "l2": "flushed between timed iterations (512 MiB write, completed before the timed region starts)", "sharding": f"index range x{world}, host sum of partials"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": stats2_bytes(st2, "h2d_bytes") * world,
                     "d2h_bytes_per_step": stats2_bytes(st2, "d2h_bytes") * world, "ms_per_step": tot_e2e / args.steps,
