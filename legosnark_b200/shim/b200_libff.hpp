@@ -201,18 +201,19 @@ inline FieldT eval_mle(const std::vector<FieldT> &v, const std::vector<FieldT> &
     return out;
 }
 
-// A commitment key kept on the device (CommScheme's g1s, LS/prototools/commit.h:129-147)
+// A commitment key kept on the device (CommScheme's g1s / g2s, LS/prototools/commit.h:129-147): uploaded and
+// normalised once; msm() is then CommScheme::commit's multiExpMA(g1s, v) / multiExpMA(g2s, v) (commit.h:149-158)
+// moving only the scalars.  precompute() adds the window multiples (b200_key_precompute_*).
 template <typename T>
 struct resident_key {
     uint64_t handle = 0;
     size_t n = 0;
     explicit resident_key(const std::vector<T> &bases) : n(bases.size())
     {
-        static_assert(group_traits<T>::group == 0, "resident_key<T>: G1 keys (CPPoly::prove uses g1s)");
         ensure_init();
-        if (b200_device_count() != 1)
-            throw std::runtime_error("resident_key: b200_cppoly_prove_g1 needs a single-device engine (set B200_GPUS=1)");
-        check(b200_pin_bases_g1(n ? limbs_of(bases.data()) : nullptr, n, &handle), "b200_pin_bases_g1");
+        check(group_traits<T>::group == 0 ? b200_pin_bases_g1(n ? limbs_of(bases.data()) : nullptr, n, &handle)
+                                          : b200_pin_bases_g2(n ? limbs_of(bases.data()) : nullptr, n, &handle),
+              "b200_pin_bases");
     }
     ~resident_key()
     {
@@ -220,6 +221,24 @@ struct resident_key {
     }
     resident_key(const resident_key &) = delete;
     resident_key &operator=(const resident_key &) = delete;
+
+    void precompute(uint32_t window_bits = 0)
+    {
+        check(group_traits<T>::group == 0 ? b200_key_precompute_g1(handle, window_bits) : b200_key_precompute_g2(handle, window_bits),
+              "b200_key_precompute");
+    }
+    // sum_i v[i] * bases[i] over the first min(n, v.size()) bases (multiExpMA's n = min(sizes), LS/utils/globl.h:63-78)
+    template <typename FieldT>
+    T msm(const std::vector<FieldT> &v) const
+    {
+        static_assert(std::is_same<FieldT, typename T::scalar_field>::value && sizeof(FieldT) == 32, "scalars must be the group's Fr");
+        const size_t m = v.size() < n ? v.size() : n;
+        uint64_t out[24];
+        const uint64_t *s = m ? reinterpret_cast<const uint64_t *>(v.data()) : nullptr;
+        check(group_traits<T>::group == 0 ? b200_msm_pinned_g1(handle, 0, s, m, out) : b200_msm_pinned_g2(handle, 0, s, m, out),
+              "b200_msm_pinned");
+        return point_from_limbs<T>(out);
+    }
 };
 
 // CPPoly::prove (LS/gadgets/poly.h:45-91): witness[i] for i < d; witnessa[i] (i >= 1) equals witness[i]
@@ -228,6 +247,8 @@ template <typename T, typename FieldT>
 inline std::vector<T> cppoly_prove(const resident_key<T> &key, const std::vector<FieldT> &v, const std::vector<FieldT> &r)
 {
     static_assert(std::is_same<FieldT, typename T::scalar_field>::value && sizeof(FieldT) == 32, "scalars must be the group's Fr");
+    static_assert(group_traits<T>::group == 0, "CPPoly::prove commits in G1");
+    if (b200_device_count() != 1) throw std::runtime_error("cppoly_prove: b200_cppoly_prove_g1 needs a single-device engine (set B200_GPUS=1)");
     const size_t d = r.size();
     if (v.size() != ((size_t)1 << d)) throw std::runtime_error("CPPoly::prove: expected v.size() == 1 << d");
     std::vector<uint64_t> out(12 * d);
