@@ -39,6 +39,12 @@ def test_no_cpu_fallback():
         lb.multi_exp("g1", P, s)
     with pytest.raises(lb.B200Error):
         lb.batch_to_special("g1", P)
+    # the Fr-side and wire-format entry points refuse as well: nothing is computed on the host
+    v = np.zeros((4, 4), dtype=np.uint64)
+    for call in (lambda: lb.evalMLE(v, v[:2]), lambda: lb.fold_witness(v, v[:2]), lambda: lb.mle_push_randomness(v, v[:1]),
+                 lambda: lb.fr_fft(v, lb.FFT), lambda: lb.compress_points("g1", P), lambda: lb.decompress_points("g1", s, np.zeros(1, np.uint8))):
+        with pytest.raises(lb.B200Error, match="b200_init has not been called"):
+            call()
 
 
 def test_product_never_imports_the_oracle():
