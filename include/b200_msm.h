@@ -1,5 +1,8 @@
 /* b200_msm.h — C-ABI of the B200-native MSM / fixed-base batch_exp engine that
- * drops in behind libff's scalar_multiplication templates as used by LegoSNARK.
+ * drops in behind libff's scalar_multiplication templates as used by LegoSNARK,
+ * plus the neighbours of that path: the knowledge-commitment MSM,
+ * the Fr vector work of CPPoly / sum-check tables, libfqfft's radix-2 transform and
+ * the point compression of the stream operators.
  *
  * The reference has no FFI: its boundary is a set of C++ function templates in
  *   LFF/algebra/scalar_multiplication/multiexp.hpp
