@@ -22,9 +22,18 @@ the device by the fixed-base kernel.  Numbers on the JSON line:
   cpu_baseline  libff's multi_exp<BDLO12> (oracle/_ref, built from the unmodified reference)
           on this box's host cores over a bounded sample of the same workload.
 
-With N > 1 (torchrun) every rank owns the index range of an N * 2^log2n-point MSM
-(weak scaling): it runs the whole pipeline on its slice, the 96-byte partials are
-all-gathered and summed on the host (no data-path collective).
+  e2e_pageable  as e2e, but from plain (pageable) numpy buffers — what a libff caller's std::vector is.
+
+With N > 1 (torchrun) every rank owns the index range of an N * 2^log2n-point MSM (weak scaling, the
+default) or of ONE 2^log2n-point MSM (--scaling strong: the reference's own split, multiexp.tcc:417-438):
+it runs the whole pipeline on its slice, the 96-byte partials go through a page of host shared memory
+(legosnark_b200.multi.HostMailbox) and are summed on the host — no collective, no NCCL in the data path
+(torch.distributed only lines the ranks up before a step and takes the max of the timings afterwards).
+
+--impl reference times libff's multi_exp<BDLO12> (oracle/_ref = the unmodified reference sources) with
+chunks = all host threads on the SAME workload (2^log2n points per step by default), trying both of the
+reference's curve builds (alt_bn128 + USE_ASM, and bn128 = ate-pairing's Xbyak JIT, LegoSNARK's default
+CURVE) and the -march=native build when it runs on this host; the faster combination is the one timed.
 """
 from __future__ import annotations
 
@@ -71,6 +80,19 @@ def random_scalars(n, seed):
     a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
     a[:, 3] &= np.uint64((1 << 61) - 1)
     return a
+
+
+def workload_config(args, world):
+    """The `config` object: identical for the GPU arm and the reference arm of one (group, log2n, scaling, N)."""
+    per = f"2^{args.log2n} points per GPU" if args.scaling == "weak" else f"one MSM of 2^{args.log2n} points split over the GPUs by index range"
+    return {"workload": f"{args.group} MSM, {per} (BASELINE.json configs[1] at 2^20; configs[4] for the other sizes / G2)",
+            "group": args.group, "log2n": args.log2n, "n_gpus": world, "scaling": args.scaling,
+            "scalars": "uniform 253-bit", "bases": "k_i*G, distinct",
+            "key": "GPU arm `value`: precomputed resident key (window multiples 2^(c k) P_i kept in HBM, one-off cost reported in "
+                   "plain_key.key_precompute_ms_one_off); `plain_key`: plain resident affine key; `e2e`: cold host bases + scalars "
+                   "through b200_msm_*; reference arm: libff multi_exp<BDLO12> on host vectors",
+            "l2": "GPU arm: flushed between timed iterations (512 MiB write, completed before the timed region starts)",
+            "sharding": "index range per rank, partials summed on the host (no collective)"}
 
 
 class ClockSampler:
@@ -133,43 +155,62 @@ def ncu_traffic(group, log2n, pre=False):
         return None
 
 
-def checker():
+def checker(native=False):
     from oracle.binding import Checker
     if Checker.available("ref"):
         try:
-            return Checker("ref"), "reference"
+            return Checker("ref", native=native), "reference"
         except Exception:
             pass
     return Checker("orc"), "port"
 
 
 def run_reference(args, rank, world):
-    """--impl reference: libff multi_exp<BDLO12> with chunks = host threads, bounded sample per step."""
+    """--impl reference: libff multi_exp<BDLO12> with chunks = host threads on the arm's workload."""
     if rank != 0:
         return
-    chk, kind = checker()
+    from oracle.binding import Checker
+    chk, kind = checker(native=True)
     group = args.group
     m = 1 << min(args.log2n, args.ref_log2n)
     k = chk.sha512_rng_fr(1 << 40, m)
     P = chk.batch_exp(group, chk.one(group), k, normalise=True)
     s = chk.sha512_rng_fr(0, m)
     threads = chk.max_threads()
+    # which of the reference's builds is faster here: alt_bn128 (x86-64 asm Fp) or bn128 (Xbyak JIT Fp, LegoSNARK's default
+    # CURVE); one probe each on a 2^16 prefix, then every timed step runs the winner
+    probes = {}
+    if kind == "reference":
+        mp_ = min(m, 1 << 16)
+        for name, curve in (("alt_bn128+USE_ASM", 0), ("bn128 (Xbyak JIT)", 1)):
+            chk.msm(group, P[:mp_], s[:mp_], chunks=threads, variant=0, curve=curve)
+            t0 = time.perf_counter()
+            chk.msm(group, P[:mp_], s[:mp_], chunks=threads, variant=0, curve=curve)
+            probes[name] = mp_ / (time.perf_counter() - t0)
+        best = max(probes, key=probes.get)
+        curve = 0 if best.startswith("alt") else 1
+    else:
+        best, curve = "C restatement of alt_bn128", 0
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        chk.msm(group, P, s, chunks=threads, variant=0)
+        if kind == "reference":
+            chk.msm(group, P, s, chunks=threads, variant=0, curve=curve)
+        else:
+            chk.msm(group, P, s, chunks=threads, variant=0)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = m / (ms * 1e-3)
-    sample = f"{group} multi_exp<BDLO12> of 2^{int(np.log2(m))} points per step, chunks={threads}"
+    sample = (f"{group} multi_exp<BDLO12> of 2^{int(np.log2(m))} points per step, chunks={threads}, build: {best}"
+              f"{', -march=native' if getattr(chk, 'native', False) else ''}; probes (points/s at 2^16): "
+              + ", ".join(f"{a}: {b:.3g}" for a, b in probes.items()))
     print(json.dumps({
         "impl": "reference", "metric": METRIC.replace("g1", group), "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u64 limbs (254-bit modular integer)", "data": "synthetic",
-        "config": {"workload": f"{group} MSM 2^{args.log2n} points per GPU (BASELINE.json configs[1])",
-                   "reference_sample_points": m},
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -183,7 +224,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=20, help="points per GPU = 2^log2n")
     ap.add_argument("--group", default="g1", choices=["g1", "g2"])
-    ap.add_argument("--ref-log2n", type=int, default=17, help="sample size of the CPU reference legs")
+    ap.add_argument("--ref-log2n", type=int, default=20, help="cap on the size of one step of the reference arm (2^20 = 1.5 s per step)")
+    ap.add_argument("--cpu-sample-log2n", type=int, default=18, help="sample of the in-arm cpu_baseline / parity leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 2^log2n points per GPU; strong: one 2^log2n-point MSM split over the GPUs")
+    ap.add_argument("--transport", default="mailbox", choices=["mailbox", "nccl"], help="how the 96-byte partials travel")
+    ap.add_argument("--no-cplink", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true",
                     help="headline on the plain resident key (default: key extended by b200_key_precompute_*)")
@@ -218,7 +264,20 @@ def main():
     lb.init_devices([local_rank])
 
     group = args.group
-    n = 1 << args.log2n
+    if args.scaling == "weak":
+        n = 1 << args.log2n
+    else:  # strong: this rank's index range of ONE 2^log2n-point MSM (multiexp.tcc:417-431: the last chunk takes the remainder)
+        lo_, hi_ = lb.shard_range(1 << args.log2n, rank, world)
+        n = hi_ - lo_
+    n_total = world * n if args.scaling == "weak" else 1 << args.log2n
+    mailbox = None
+    if world > 1 and args.transport == "mailbox":
+        name = f"b200_partials_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'run')}"
+        if rank == 0:
+            mailbox = multi.HostMailbox(name, rank, world, create=True)
+        dist.barrier()
+        if rank != 0:
+            mailbox = multi.HostMailbox(name, rank, world, create=False)
     L = 12 if group == "g1" else 24
     A = 8 if group == "g1" else 16
     stream = torch.cuda.current_stream().cuda_stream
@@ -242,6 +301,8 @@ def main():
     del d_k, d_aff
     s_np = s_host.numpy().view(np.uint64)
     jac_np = jac_host.numpy().view(np.uint64)
+    # the same inputs in pageable memory (what a libff caller's std::vector is)
+    s_page, jac_page = np.array(s_np), np.array(jac_np)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -267,7 +328,7 @@ def main():
         ev1.synchronize()
         dev_ms = ev0.elapsed_time(ev1)
         t0 = time.perf_counter()
-        res = multi.sharded_multi_exp(group, part, dev) if world > 1 else part
+        res = multi.sharded_multi_exp(group, part, dev, mailbox) if world > 1 else part
         gather_ms = (time.perf_counter() - t0) * 1e3 if world > 1 else 0.0
         return res, dev_ms + gather_ms, lb.last_stats()
 
@@ -278,16 +339,18 @@ def main():
         align()
         t0 = time.perf_counter()
         part = key.multi_exp(s_np)
-        res = multi.sharded_multi_exp(group, part, dev) if world > 1 else part
+        res = multi.sharded_multi_exp(group, part, dev, mailbox) if world > 1 else part
         return res, (time.perf_counter() - t0) * 1e3, lb.last_stats()
 
-    def step_e2e():
+    def step_e2e(bases=None, scalars=None):
+        bases = jac_np if bases is None else bases
+        scalars = s_np if scalars is None else scalars
         flush.zero_()
         torch.cuda.synchronize()
         align()
         t0 = time.perf_counter()
-        part = lb.multi_exp(group, jac_np, s_np)
-        res = multi.sharded_multi_exp(group, part, dev) if world > 1 else part
+        part = lb.multi_exp(group, bases, scalars)
+        res = multi.sharded_multi_exp(group, part, dev, mailbox) if world > 1 else part
         return res, (time.perf_counter() - t0) * 1e3, lb.last_stats()
 
     # ---- measured denominators -------------------------------------------------------
@@ -317,7 +380,7 @@ def main():
         t0 = time.perf_counter()
         key.precompute(args.precompute_bits)
         pre_ms = (time.perf_counter() - t0) * 1e3
-        plain = {"value": world * n / (tot_pl / args.steps * 1e-3), "unit": UNIT, "ms_per_step": tot_pl / args.steps,
+        plain = {"value": n_total / (tot_pl / args.steps * 1e-3), "unit": UNIT, "ms_per_step": tot_pl / args.steps,
                  "window_bits": stp["window_bits"], "windows": stp["num_windows"], "k_accumulate_ms": float(np.mean(pl_acc)),
                  "mixed_adds": stp["num_entries"], "key_precompute_ms_one_off": pre_ms}
 
@@ -359,17 +422,26 @@ def main():
         e2r_ms.append(ms)
     barrier()
     assert (res3 == result).all(), "resident-key host-scalar path disagrees"
+    for _ in range(min(args.warmup, 3)):
+        step_e2e(jac_page, s_page)
+    barrier()
+    e2p_ms = []
+    for _ in range(args.steps):
+        res4, ms, st4 = step_e2e(jac_page, s_page)
+        e2p_ms.append(ms)
+    barrier()
+    assert (res4 == result).all(), "pageable host-buffer path disagrees"
     if plain is not None:
         assert (res_plain == result).all(), "precomputed key and plain key disagree"
 
-    tot_res, tot_e2e, tot_e2r = float(np.sum(res_ms)), float(np.sum(e2e_ms)), float(np.sum(e2r_ms))
+    tot_res, tot_e2e, tot_e2r, tot_e2p = float(np.sum(res_ms)), float(np.sum(e2e_ms)), float(np.sum(e2r_ms)), float(np.sum(e2p_ms))
     if world > 1:
-        t = torch.tensor([tot_res, tot_e2e, tot_e2r], dtype=torch.float64, device=dev)
+        t = torch.tensor([tot_res, tot_e2e, tot_e2r, tot_e2p], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot_res, tot_e2e, tot_e2r = float(t[0]), float(t[1]), float(t[2])
+        tot_res, tot_e2e, tot_e2r, tot_e2p = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     ms_per_step = tot_res / args.steps
-    value = world * n / (ms_per_step * 1e-3)
-    e2e_value = world * n / (tot_e2e / args.steps * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
+    e2e_value = n_total / (tot_e2e / args.steps * 1e-3)
 
     # ---- roofline of the dominant kernel ---------------------------------------------
     acc = float(np.mean(acc_ms))
@@ -405,7 +477,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         chk, kind = checker()
-        m = 1 << min(args.log2n, args.ref_log2n + 1)
+        m = min(n, 1 << args.cpu_sample_log2n)
         threads = chk.max_threads()
         t0 = time.perf_counter()
         want = chk.msm(group, jac_np[:m], s_np[:m], chunks=threads, variant=0)
@@ -413,7 +485,7 @@ def main():
         got = key.multi_exp(s_np[:m])
         assert (got == want).all(), "GPU result differs from the CPU reference on the baseline sample"
         cpu = {"value": m / dt, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"first 2^{int(np.log2(m))} points of the workload, multi_exp<BDLO12> chunks={threads}, {dt:.2f} s; "
+               "sample": f"first {m} points of the workload, multi_exp<BDLO12> chunks={threads}, {dt:.2f} s; "
                          "GPU result on the same sample bit-identical"}
 
     # ---- the other half of BASELINE.json's metric: cplink prove ms, from the end-to-end driver over the
@@ -422,26 +494,29 @@ def main():
     key.close()
     lb.shutdown()
     cplink = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_cplink:
         cplink = cplink_prove_ms()
+    if mailbox is not None:
+        mailbox.close(unlink=rank == 0)
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC.replace("g1", group), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u32 limbs (254-bit modular integer, 8x32-bit Montgomery)", "data": "synthetic",
-            "config": {"workload": f"{group} MSM 2^{args.log2n} points per GPU (BASELINE.json configs[1])",
-                       "points_per_gpu": n, "window_bits": stats["window_bits"], "windows": stats["num_windows"],
-                       "scalars": "uniform 253-bit", "bases": "k_i*G, distinct, resident in HBM for `value`",
+            "config": workload_config(args, world),
+            "engine": {"points_this_rank": n, "points_total": n_total, "window_bits": stats["window_bits"], "windows": stats["num_windows"],
                        "key": ("plain affine key" if plain is None else
-                               f"precomputed key: window multiples 2^(c k) P_i resident in HBM ({stats['num_windows']} x 64 B per base), "
-                               "all windows share one bucket set; one-off cost in plain_key.key_precompute_ms_one_off"),
-                       "l2": "flushed between timed iterations (512 MiB write, completed before the timed region starts)", "sharding": f"index range x{world}, host sum of partials"},
+                               f"precomputed key: {stats['num_windows']} levels x 64 B per base resident in HBM, all windows share one bucket set"),
+                       "partials": ("host shared memory (HostMailbox)" if mailbox is not None else "n/a (one rank)" if world == 1 else "NCCL all_gather")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": stats2_bytes(st2, "h2d_bytes") * world,
                     "d2h_bytes_per_step": stats2_bytes(st2, "d2h_bytes") * world, "ms_per_step": tot_e2e / args.steps,
                     "path": "b200_msm_* with pinned host Jacobian bases + scalars (cold key)"},
-            "e2e_resident_key": {"value": world * n / (tot_e2r / args.steps * 1e-3), "unit": UNIT, "ms_per_step": tot_e2r / args.steps,
+            "e2e_pageable": {"value": n_total / (tot_e2p / args.steps * 1e-3), "unit": UNIT, "ms_per_step": tot_e2p / args.steps,
+                             "h2d_bytes_per_step": stats2_bytes(st4, "h2d_bytes") * world, "d2h_bytes_per_step": stats2_bytes(st4, "d2h_bytes") * world,
+                             "path": "b200_msm_* from pageable host buffers (a libff caller's std::vector): staged through pinned chunks inside the call"},
+            "e2e_resident_key": {"value": n_total / (tot_e2r / args.steps * 1e-3), "unit": UNIT, "ms_per_step": tot_e2r / args.steps,
                                  "h2d_bytes_per_step": float(st3["h2d_bytes"]) * world, "d2h_bytes_per_step": float(st3["d2h_bytes"]) * world,
                                  "path": "b200_msm_pinned_*: pinned host scalars against the key resident in HBM (a commitment under a fixed key)"},
             "gpu_launches": int(stats["kernel_launches"]) * args.steps,

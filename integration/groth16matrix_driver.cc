@@ -14,12 +14,17 @@
 // the generator's are batch_exp / batch_exp_with_coeff / kc_batch_exp / batch_to_special,
 // :296-360.  In the b200 build each prover MSM is also recomputed with the reference's own
 // template (still reachable as libff::libff_cpu_* / libsnark::libsnark_cpu_*) on the same key and
-// witness and compared as group elements ("parity" in the JSON line) when n <= parity_max_n.
+// witness and compared as group elements ("parity" in the JSON line) when n <= parity_max_n; the
+// reference templates run with chunks = omp_get_max_threads() (multiexp.tcc:417-438), which keeps the
+// check affordable at n = 128 (2.1 M constraints).  The proof itself cannot be compared between
+// builds: the prover draws r, s from std::random_device (r1cs_gg_ppzksnark.tcc:417-418).
 //
-//   groth16matrix_{cpu,cpuomp,b200} [n = 16] [parity_max_n = 32]
+//   groth16matrix_{cpu,cpuomp,b200} [n = 16] [parity_max_n = 128]
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
+#include <omp.h>
 using namespace std;
 
 #include "globl.h"
@@ -42,7 +47,7 @@ static unsigned rand32b() { return (unsigned)(rand() % 0xFFFFFFFF); }  // legogr
 int main(int argc, char **argv)
 {
     const int n = argc > 1 ? atoi(argv[1]) : 16;
-    const int parity_max_n = argc > 2 ? atoi(argv[2]) : 32;
+    const int parity_max_n = argc > 2 ? atoi(argv[2]) : 128;
     libff::inhibit_profiling_info = getenv("B200_DRIVER_PROFILE") == nullptr;  // libff's enter/leave_block timings
     libff::inhibit_profiling_counters = true;
     ppT::init_public_params();
@@ -123,16 +128,17 @@ int main(int argc, char **argv)
         cw.insert(cw.end(), full.begin(), full.end());
         const auto &pk = keypair.pk;
         const size_t nv = cw.size();
+        const size_t ch = (size_t)omp_get_max_threads();
         const libff::G1<ppT> a_gpu = libff::multi_exp_with_mixed_addition<libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
             pk.A_query.begin(), pk.A_query.begin() + nv, cw.begin(), cw.end(), 1);
         const libff::G1<ppT> a_cpu = libff::libff_cpu_multi_exp_with_mixed_addition<libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
-            pk.A_query.begin(), pk.A_query.begin() + nv, cw.begin(), cw.end(), 1);
+            pk.A_query.begin(), pk.A_query.begin() + nv, cw.begin(), cw.end(), ch);
         const auto b_gpu = kc_multi_exp_with_mixed_addition<libff::G2<ppT>, libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
             pk.B_query, 0, nv, cw.begin(), cw.end(), 1);
         const auto b_cpu = libsnark_cpu_kc_multi_exp_with_mixed_addition<libff::G2<ppT>, libff::G1<ppT>, FieldT, libff::multi_exp_method_BDLO12>(
-            pk.B_query, 0, nv, cw.begin(), cw.end(), 1);
+            pk.B_query, 0, nv, cw.begin(), cw.end(), ch);
         const libff::G1<ppT> c_cpu = libff::libff_cpu_multi_exp_with_mixed_addition<LG1, LFr, libff::multi_exp_method_BDLO12>(
-            u1.begin(), u1.end(), e1.begin(), e1.end(), 1);
+            u1.begin(), u1.end(), e1.begin(), e1.end(), ch);
         parity = (a_gpu == a_cpu && b_gpu.g == b_cpu.g && b_gpu.h == b_cpu.h && c_cpu == res1) ? "identical" : "MISMATCH";
     } else {
         parity = "skipped";

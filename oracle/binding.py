@@ -23,6 +23,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORC_PATH = os.path.join(HERE, "libbn254oracle.so")
 REF_PATH = os.path.join(HERE, "_ref", "libffref.so")
+REF_NATIVE_PATH = os.path.join(HERE, "_ref", "libffref_native.so")  # same sources, -march=native (timed baseline only)
 LSREF_PATH = os.path.join(HERE, "_ref", "liblsref.so")  # oracle/ref_wrap_ls.cpp: LegoSNARK / libfqfft Fr-side routines
 
 _u64p = ctypes.POINTER(ctypes.c_uint64)
@@ -44,6 +45,20 @@ def build_ref() -> str | None:
     return REF_PATH if os.path.exists(REF_PATH) else None
 
 
+def native_build_runs() -> bool:
+    """The -march=native build was compiled in the build container; run a tiny MSM with it in a child process
+    so that an instruction this host lacks ends the child, not the caller."""
+    code = ("import ctypes, numpy as np; L = ctypes.CDLL(%r); L.ref_init(); o = np.zeros(12, dtype=np.uint64); "
+            "b = np.zeros((4, 12), dtype=np.uint64); s = np.zeros((4, 4), dtype=np.uint64); "
+            "p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)); "
+            "raise SystemExit(L.ref_msm_g1(0, p(b), p(s), ctypes.c_size_t(4), ctypes.c_size_t(1), 0, 1, p(o)))" % REF_NATIVE_PATH)
+    try:
+        import sys
+        return subprocess.run([sys.executable, "-c", code], capture_output=True, timeout=120).returncode == 0
+    except Exception:
+        return False
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_u64p)
 
@@ -58,9 +73,10 @@ def _c(a, width=None):
 class Checker:
     """Uniform view over the restatement ("orc") and the compiled reference ("ref")."""
 
-    def __init__(self, kind: str = "orc"):
+    def __init__(self, kind: str = "orc", native: bool = False):
         assert kind in ("orc", "ref")
         self.kind = kind
+        self.native = False
         if kind == "orc":
             if not os.path.exists(ORC_PATH) or os.path.getmtime(ORC_PATH) < os.path.getmtime(
                 os.path.join(HERE, "bn254_oracle.c")
@@ -74,6 +90,8 @@ class Checker:
             if not os.path.exists(REF_PATH):
                 raise FileNotFoundError("oracle/_ref/libffref.so not built (needs /root/reference)")
             path = REF_PATH
+            if native and os.path.exists(REF_NATIVE_PATH) and native_build_runs():
+                path, self.native = REF_NATIVE_PATH, True
         self.lib = ctypes.CDLL(path)
         self.p = kind + "_"
         self.curve_arg = kind == "ref"

@@ -71,6 +71,39 @@ def scalar_sum_check(chk, group, k, s):
     return chk.scalar_mul(group, chk.one(group), ints_to_mont([tot], R_ORDER), normalise=True)[0]
 
 
+def fr_fast_uniform(n, seed=0):
+    """Uniform 253-bit integers read as Montgomery images (every residue below r is one): numpy's generator, for
+    the 2^22..2^26 cases where SHA512_rng's one hash per element would take minutes."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)
+    return a
+
+
+def scalar_sum_fast(k, s):
+    """sum k_i s_i mod r for Montgomery-form limb arrays, exact and vectorised: both vectors are cut into 16-bit
+    pieces, the 16 x 16 piece-by-piece dot products run as float64 matrix products over chunks of 2^19 rows
+    (every partial sum stays below 2^51, so the floating-point sums are exact), and the pieces are recombined
+    with Python integers.  Returns the plain (non-Montgomery) integer."""
+    k = np.ascontiguousarray(k, dtype=np.uint64).view(np.uint16).reshape(len(k), 16)
+    s = np.ascontiguousarray(s, dtype=np.uint64).view(np.uint16).reshape(len(s), 16)
+    acc = [[0] * 16 for _ in range(16)]
+    step = 1 << 19
+    for lo in range(0, len(k), step):
+        m = k[lo:lo + step].astype(np.float64).T @ s[lo:lo + step].astype(np.float64)
+        for a in range(16):
+            for b in range(16):
+                acc[a][b] += int(m[a, b])
+    tot = sum(acc[a][b] << (16 * (a + b)) for a in range(16) for b in range(16))
+    rinv = pow(MONT_R, -1, R_ORDER)
+    return tot * rinv * rinv % R_ORDER
+
+
+def scalar_sum_point(chk, group, k, s):
+    """(sum s_i k_i mod r) * G as a normalised point: SURVEY.md 8(c)'s independent oracle at any n."""
+    return chk.scalar_mul(group, chk.one(group), ints_to_mont([scalar_sum_fast(k, s)], R_ORDER), normalise=True)[0]
+
+
 def msm_cases(chk, group, sizes=(0, 1, 2, 3, 17, 64, 257)):
     """Named (bases, scalars) cases covering SURVEY.md §8(d)'s distributions and edge corpus."""
     nmax = max(max(sizes), 64)

@@ -252,6 +252,67 @@ def test_scalar_sum_identity_at_scale(engine, orc, grp, log2n):
     key.close()
 
 
+def _device_bases(engine, orc, grp, k):
+    """P_i = k_i G made by the GPU fixed-base path, spot-checked against the oracle."""
+    n = len(k)
+    table = engine.get_window_table(grp, 254, 0, orc.one(grp), expected_scalars=n)
+    P = engine.batch_exp(254, 0, table, k)
+    table.close()
+    idx = np.r_[0:32, n - 32:n, np.random.default_rng(1).integers(0, n, 192)]
+    assert (P[idx] == orc.batch_exp(grp, orc.one(grp), k[idx])).all()
+    return P
+
+
+@pytest.mark.parametrize("grp,log2n", [("g1", 22), ("g1", 24), ("g2", 18), ("g2", 20)])
+def test_scalar_sum_identity_config5_sizes(engine, orc, grp, log2n):
+    """BASELINE.json configs[4] sizes (G1 up to 2^24 here, G2 2^20): the host-buffer path, the plain resident
+    key and the precomputed key (the engine's own window choice: c = 20 at these sizes) against the
+    scalar-sum identity, whose right-hand side is computed exactly on the host (tests/inputs.py)."""
+    n = 1 << log2n
+    k = inputs.fr_fast_uniform(n, seed=601 + log2n)
+    s = inputs.fr_fast_uniform(n, seed=602 + log2n)
+    P = _device_bases(engine, orc, grp, k)
+    want = inputs.scalar_sum_point(orc, grp, k, s)
+    assert (engine.multi_exp(grp, P, s) == want).all(), "host-buffer path"
+    key = engine.CommitmentKey(grp, P)
+    try:
+        del P
+        assert (key.multi_exp(s) == want).all(), "plain resident key"
+        key.precompute()
+        assert (key.multi_exp(s) == want).all(), "precomputed key"
+        assert engine.last_stats()["num_windows"] * engine.last_stats()["window_bits"] >= 254
+        # a skewed vector at the same size: 32-bit scalars (rand32b, legogrothmatrix.cc:29-32)
+        small = np.zeros((n, 4), dtype=np.uint64)
+        small[:, 0] = np.random.default_rng(5).integers(0, 1 << 32, size=n, dtype=np.uint64)
+        s32 = orc.fr_from_bigint(small)
+        assert (key.multi_exp(s32) == inputs.scalar_sum_point(orc, grp, k, s32)).all(), "32-bit scalars"
+    finally:
+        key.close()
+
+
+@pytest.mark.parametrize("grp,log2n", [("g1", 15), ("g2", 13)])
+def test_precomputed_window_22(engine, orc, grp, log2n):
+    """choose_precompute_window picks c = 22 from 2^25 bases on (12 levels, 2^21 buckets); that geometry is run
+    here on a key small enough for the driver's suite, forced through b200_key_precompute_*(22)."""
+    n = 1 << log2n
+    k = inputs.fr_uniform(orc, n, seed=611)
+    P = _device_bases(engine, orc, grp, k)
+    key = engine.CommitmentKey(grp, P)
+    try:
+        key.precompute(22)
+        engine.set_tuning_ex("use_precomputed", 2)
+        for s in (inputs.fr_uniform(orc, n, seed=612), inputs.fr_zero_one_heavy(orc, n, seed=613)):
+            assert (key.multi_exp(s) == inputs.scalar_sum_point(orc, grp, k, s)).all()
+            st = engine.last_stats()
+            assert st["window_bits"] == 22 and st["num_windows"] == 12
+        m = n // 2 + 5
+        s = inputs.fr_uniform(orc, m, seed=614)
+        assert (key.multi_exp(s, offset=77) == inputs.scalar_sum_point(orc, grp, k[77:77 + m], s)).all()
+    finally:
+        engine.set_tuning_ex("use_precomputed", 1)
+        key.close()
+
+
 @pytest.mark.parametrize("n", [0, 1, 65, 1026, 6000])
 def test_knowledge_commitment_pair(engine, orc, n):
     """knowledge_commitment<G2,G1> MSM (SNK/knowledge_commitment/kc_multiexp.tcc:21-89: the B query

@@ -63,6 +63,53 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
+def _mailbox_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle.binding import Checker
+    import legosnark_b200 as lb
+    from legosnark_b200 import multi
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    name = f"b200_test_partials_{port}"
+    box = multi.HostMailbox(name, rank, world, create=True) if rank == 0 else None
+    dist.barrier()
+    if box is None:
+        box = multi.HostMailbox(name, rank, world, create=False)
+    orc = Checker("orc")
+    got = []
+    for step, grp in enumerate(("g1", "g2", "g1", "g1")):  # several steps: the slots alternate and are reused
+        m = n if grp == "g1" else n // 4
+        P, _ = inputs.bases(orc, grp, m, seed=81 + step)
+        s = inputs.fr_uniform(orc, m, seed=91 + step)
+        lo, hi = lb.shard_range(m, rank, world)
+        total = multi.sharded_multi_exp(grp, orc.msm(grp, P[lo:hi], s[lo:hi]), mailbox=box)
+        got.append((total, orc.msm(grp, P, s, chunks=world)))
+    if rank == 0:
+        q.put(got)
+    dist.barrier()
+    box.close(unlink=rank == 0)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_host_mailbox():
+    """The partials travel through host shared memory (no collective): what bench.py uses under torchrun."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mailbox_worker, args=(r, 2, port, 203, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for total, want in got:
+        assert (total == want).all()
+
+
 def test_world_size_2_gloo():
     import torch.multiprocessing as mp
     with socket.socket() as s:
