@@ -74,6 +74,19 @@ int b200_msm_g2(const uint64_t *bases /* n x 24 */, const uint64_t *scalars_mont
 int b200_msm_g2g1(const uint64_t *g2_bases /* n x 24 */, const uint64_t *g1_bases /* n x 12 */,
                   const uint64_t *scalars_mont /* n x 4 */, size_t n, uint64_t out_g2[24], uint64_t out_g1[12]);
 
+/* Many small MSMs in ONE call: out[j] = sum_{i in [offsets[j], offsets[j+1])} scalars[i] * bases[i], j < count.
+ * Replaces the loop of tiny multi_exp calls behind LegoSNARK's sparse-matrix keygen: mtxmultiexp
+ * (LS/gadgets/subspace.cc:18-25) calls simplesparsemexp -> sparsemexpG -> multi_exp<BDLO12>
+ * (LS/utils/sparsemexp.h:62-90, sparsemexp.cc:15-24) once per matrix column, 2 050 columns of one or two terms for
+ * the shipped cplink example.  One thread per term runs a 4-bit windowed scalar multiplication, one thread per
+ * MSM sums its terms, the outputs are normalised together (one shared inversion per thread block of outputs);
+ * the host sees one upload, one kernel chain and one download instead of `count` round trips.
+ * offsets: count + 1 non-decreasing indices, offsets[0] = 0; outputs are normalised like b200_msm_*. */
+int b200_msm_batch_g1(const uint64_t *bases /* offsets[count] x 12 */, const uint64_t *scalars_mont /* offsets[count] x 4 */,
+                      const uint64_t *offsets /* count + 1 */, size_t count, uint64_t *out /* count x 12 */);
+int b200_msm_batch_g2(const uint64_t *bases /* offsets[count] x 24 */, const uint64_t *scalars_mont,
+                      const uint64_t *offsets, size_t count, uint64_t *out /* count x 24 */);
+
 /* Host-side sum of partial results (north star: "each GPU returns a partial group element,
  * and the partials are summed on the host"; the serial sum at multiexp.tcc:433-438).  Used by
  * the engine for its own per-device partials and by one-process-per-GPU launchers (bench.py
@@ -167,6 +180,33 @@ int b200_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_
 int b200_fr_eval_mle(const uint64_t *v /* 2^d x 4 */, const uint64_t *r /* d x 4 */, size_t d, uint64_t out[4]);
 /* DPMle::pushRandomness (LS/prototools/mle.h:199-210): out[p] = table[p] (1 - r) + table[p + half] r. */
 int b200_fr_mle_bind(const uint64_t *table /* 2 half x 4 */, size_t half, const uint64_t r[4], uint64_t *out /* half x 4 */);
+/* step_radix2_domain::divide_by_Z_on_coset (FQFFT/evaluation_domain/domains/step_radix2_domain.tcc:213-241; FQFFT =
+ * depends/libsnark/depends/libfqfft/libfqfft): the domain libfqfft picks for 2^k + 2^r constraints (the 128 x 128 matrix
+ * product of BASELINE.json configs[3]: 2^21 + 1) divides by Z with ONE FIELD INVERSION PER POINT on the host, 95 % of the
+ * Groth16 prover once the MSMs and FFTs are on the device.  In place: P[i] *= (c1 * ratio^i - c0)^-1 for i < n_geo, and
+ * P[n_geo + i] *= tail for i < n_tail (tail may be NULL when n_tail == 0); the caller forms the four constants
+ * (shim/libfqfft/.../step_radix2_domain.hpp).  Batched inversion on the device; inverses are unique, so the limbs agree. */
+int b200_fr_scale_inv_geometric(uint64_t *P /* (n_geo + n_tail) x 4 */, size_t n_geo, const uint64_t c1[4], const uint64_t ratio[4],
+                                const uint64_t c0[4], size_t n_tail, const uint64_t *tail /* 4 */);
+
+/* Sum-check dynamic-programming tables (LS/prototools/mle.h, LS/gadgets/sumcheck.h; all values Montgomery-form Fr).
+ * b200_fr_eq_table: DPBeta::compute_eq_tbl (mle.h:93-105), level by level exactly as written there:
+ *   T_0 = {1};  T_{j+1}[p] = eqbit(p >= 2^j, r[j]) * T_j[p >> 1], p < 2^(j+1);  out = T_d.
+ * b200_fr_matrix_mle: DPMatrixMle's constructor (mle.h:241-259): v[r] = sum_l A[(l << d) + r] * eq[l] with
+ *   eq = the table above for rho; A is the vectorised 2^d x 2^d matrix.
+ * b200_fr_sumcheck_round: the sum over p inside CPSumcheck::make_new_h_poly (sumcheck.h:85-106) for two tables:
+ *   out = the coefficients (c0, c1, c2) of  sum_{p < half} w[p] (a[p](1-x) + a[p+half] x)(b[p](1-x) + b[p+half] x);
+ *   w = the round's beta suffix values (DPBeta::getBetaSuff) or NULL for DPBetaDummy (w = 1); the caller
+ *   multiplies by eqbit_poly(rho[j]) * beta_pre (getBetaPoly, mle.h:78-84) when there is a beta.
+ * b200_fr_sumcheck_rounds: all d rounds of the beta-less sum-check (CPSumcheckMatrix, sumcheck.h:118-131; the
+ *   loop of CPSumcheck::prove, sumcheck.cc:56-70): h[3 i .. 3 i + 2] = round i's coefficients; between rounds both
+ *   tables are bound to r[i] on the device (DPMle::pushRandomness, mle.h:199-210). */
+int b200_fr_eq_table(const uint64_t *r /* d x 4 */, size_t d, uint64_t *out /* 2^d x 4 */);
+int b200_fr_matrix_mle(const uint64_t *A /* 4^d x 4 */, const uint64_t *rho /* d x 4 */, size_t d, uint64_t *v /* 2^d x 4 */);
+int b200_fr_sumcheck_round(const uint64_t *a /* 2 half x 4 */, const uint64_t *b /* 2 half x 4 */, const uint64_t *w /* half x 4 or NULL */,
+                           size_t half, uint64_t out[12]);
+int b200_fr_sumcheck_rounds(const uint64_t *a /* 2^d x 4 */, const uint64_t *b /* 2^d x 4 */, const uint64_t *r /* d x 4 */, size_t d,
+                            uint64_t *h /* d x 12 */);
 /* CPPoly::prove (poly.h:45-91) against a resident G1 key (b200_pin_bases_g1, single device):
  * folding on the device, then witness[i] = multiExpMA(g1s, w_i) over the first 2^(d-i-1)
  * bases with the scalars never leaving the device.  witness: d normalised points; the

@@ -23,7 +23,7 @@ import numpy as np
 
 __all__ = [
     "B200Error", "init", "init_devices", "shutdown", "device_count", "lib", "library_path",
-    "multi_exp", "multi_exp_with_mixed_addition", "kc_multi_exp", "get_exp_window_size", "get_window_table", "batch_exp",
+    "multi_exp", "multi_exp_with_mixed_addition", "multi_exp_batch", "kc_multi_exp", "get_exp_window_size", "get_window_table", "batch_exp",
     "batch_exp_with_coeff", "batch_to_special", "CommitmentKey", "sum_partials", "shard_range", "WindowTable", "last_stats", "set_tuning", "set_pipeline_chunks",
     "imad_peak", "test_field_op", "test_group_op",
 ]
@@ -133,6 +133,21 @@ def multi_exp(group, bases, scalars, chunks: int = 1, method: int = multi_exp_me
         raise ValueError("bases and scalars differ in length")  # assert at multiexp.tcc:450
     out = np.zeros(L, dtype=np.uint64)
     _check(getattr(lib(), "b200_msm_" + group)(_p(bases), _p(scalars), _sz(bases.shape[0]), _p(out)), "b200_msm_" + group)
+    return out
+
+
+def multi_exp_batch(group, bases, scalars, offsets):
+    """Many small MSMs in one call: out[j] = sum over [offsets[j], offsets[j+1]) of scalars[i] * bases[i].
+    mtxmultiexp's per-column simplesparsemexp calls (LS/gadgets/subspace.cc:18-25, LS/utils/sparsemexp.h:62-90)
+    submitted together; returns (count, limbs) normalised points."""
+    L = _LIMBS[group]
+    bases, scalars = _arr(bases, L), _arr(scalars, 4)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64).reshape(-1)
+    if bases.shape[0] != scalars.shape[0] or offsets.shape[0] < 1 or int(offsets[-1]) != bases.shape[0]:
+        raise ValueError("bases, scalars and offsets disagree")
+    count = offsets.shape[0] - 1
+    out = np.zeros((count, L), dtype=np.uint64)
+    _check(getattr(lib(), "b200_msm_batch_" + group)(_p(bases), _p(scalars), _p(offsets), _sz(count), _p(out)), "b200_msm_batch_" + group)
     return out
 
 
@@ -321,6 +336,51 @@ def mle_push_randomness(table, r):
     half = table.shape[0] // 2
     out = np.zeros((half, 4), dtype=np.uint64)
     _check(lib().b200_fr_mle_bind(_p(table), _sz(half), _p(r), _p(out)), "b200_fr_mle_bind")
+    return out
+
+
+def compute_eq_tbl(r):
+    """DPBeta::compute_eq_tbl (LS/prototools/mle.h:93-105): the 2^d-entry table, level by level as the reference writes it."""
+    r = _arr(r, 4)
+    d = r.shape[0]
+    out = np.zeros((1 << d, 4), dtype=np.uint64)
+    _check(lib().b200_fr_eq_table(_p(r), _sz(d), _p(out)), "b200_fr_eq_table")
+    return out
+
+
+def matrix_mle(A, rho):
+    """DPMatrixMle's constructor (LS/prototools/mle.h:241-259): v[r] = sum_l A[(l << d) + r] * eq(rho)[l]."""
+    A, rho = _arr(A, 4), _arr(rho, 4)
+    d = rho.shape[0]
+    if A.shape[0] != 1 << (2 * d):
+        raise ValueError("A must hold 2^d x 2^d values")
+    out = np.zeros((1 << d, 4), dtype=np.uint64)
+    _check(lib().b200_fr_matrix_mle(_p(A), _p(rho), _sz(d), _p(out)), "b200_fr_matrix_mle")
+    return out
+
+
+def sumcheck_round(a, b, w=None):
+    """The sum over p inside CPSumcheck::make_new_h_poly (LS/gadgets/sumcheck.h:85-106) for two DPMle tables of
+    2 * half values; w = beta suffix values or None (DPBetaDummy).  Returns the (3, 4) coefficients."""
+    a, b = _arr(a, 4), _arr(b, 4)
+    half = a.shape[0] // 2
+    if b.shape[0] != 2 * half or (w is not None and _arr(w, 4).shape[0] != half):
+        raise ValueError("table sizes disagree")
+    w = None if w is None else _arr(w, 4)
+    out = np.zeros((3, 4), dtype=np.uint64)
+    _check(lib().b200_fr_sumcheck_round(_p(a), _p(b), _p(w), _sz(half), _p(out)), "b200_fr_sumcheck_round")
+    return out
+
+
+def sumcheck_rounds(a, b, r):
+    """All d round polynomials of the beta-less sum-check (CPSumcheckMatrix; the loop of CPSumcheck::prove,
+    LS/gadgets/sumcheck.cc:56-70), tables bound to r[i] on the device between rounds.  Returns (d, 3, 4)."""
+    a, b, r = _arr(a, 4), _arr(b, 4), _arr(r, 4)
+    d = r.shape[0]
+    if a.shape[0] != 1 << d or b.shape[0] != 1 << d:
+        raise ValueError("tables must hold 2^d values")
+    out = np.zeros((d, 3, 4), dtype=np.uint64)
+    _check(lib().b200_fr_sumcheck_rounds(_p(a), _p(b), _p(r), _sz(d), _p(out)), "b200_fr_sumcheck_rounds")
     return out
 
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200msm.so")
 OBJ = os.path.join(HERE, "build")
-UNITS = ["engine_core", "engine_g1", "engine_g2", "engine_fr", "engine_wire"]
+UNITS = ["engine_core", "engine_g1", "engine_g2", "engine_fr", "engine_wire", "engine_sort"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

@@ -84,6 +84,9 @@ struct Device {
     DevBuf scalars, bases_jac, bases_aff, flags, prefix;
     // sort
     DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, digits, meta, order, len_hist, len_cursor;
+    // radix-partition sort (engine_sort.cu): standard-form scalars, (entry, bucket) pairs, per-partition counters
+    DevBuf std_scalars, items, part;
+    bool sort_attr_set = false;
     // accumulation / reduction
     DevBuf partial, seg_run, seg_acc, job_out, split, big, done, window_sums, bucket_sum;
     // scalars equal to one, set aside by k_digit_count: index list, block partials, ticket, sum
@@ -110,7 +113,7 @@ struct Device {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
                          &entries, &digits, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
-                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big};
+                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big, &std_scalars, &items, &part};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -162,6 +165,8 @@ extern std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
 extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre, g_tune_ones, g_tune_host_horner;
+extern int g_tune_marginals;  // 1: one-window reduction by marginal sums (measured: no faster, profiles/r2c); 0 (default): bit decomposition over all segments
+extern int g_tune_sort;  // 1 (default): radix partition staged through shared memory; 0: round-1 global-atomics counting sort
 // set while the second MSM of a knowledge-commitment pair runs: every device still holds the
 // scalars of its shard in D.scalars from the first one, so the host-buffer paths skip that upload
 extern bool g_scalars_resident;
@@ -202,6 +207,7 @@ void for_each_shard(size_t nshards, Fn fn)
 // per-group entry points: templates defined in engine_impl.cuh, explicitly
 // instantiated for Fq in engine_g1.cu and for Fq2 in engine_g2.cu
 template <class F> int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out);
+template <class F> int msm_batch(const uint64_t *bases, const uint64_t *scalars, const uint64_t *offsets, size_t count, uint64_t *out);
 template <class F> int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *handle);
 template <class F> int key_precompute(uint64_t handle, uint32_t window_bits);
 template <class F> int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const void *d_scalars, size_t n,
@@ -221,6 +227,12 @@ const void *fr_fold_device(Device &D, const uint64_t *v, const uint64_t *r, size
 int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval);
 int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
 int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, void *stream);
+int fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t *c1, const uint64_t *ratio, const uint64_t *c0, size_t n_tail,
+                           const uint64_t *tail);
+int fr_eq_table(const uint64_t *r, size_t d, uint64_t *out);
+int fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v);
+int fr_sumcheck_round(const uint64_t *a, const uint64_t *b, const uint64_t *w, size_t half, uint64_t *out);
+int fr_sumcheck_rounds(const uint64_t *a, const uint64_t *b, const uint64_t *r, size_t d, uint64_t *h);
 void fr_release();
 // point (de)compression (engine_wire.cu)
 int compress_g1(const uint64_t *pts, size_t n, int fl, uint64_t *x, uint8_t *flags);

@@ -30,6 +30,7 @@ std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1, g_tune_host_horner = 1;
+int g_tune_sort = 1, g_tune_marginals = 0;
 bool g_scalars_resident = false;
 
 static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal
@@ -223,6 +224,17 @@ int b200_msm_g2g1(const uint64_t *g2_bases, const uint64_t *g1_bases, const uint
     return rc;
 }
 
+int b200_msm_batch_g1(const uint64_t *bases, const uint64_t *scalars, const uint64_t *offsets, size_t count, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_batch<Fq>(bases, scalars, offsets, count, out);
+}
+int b200_msm_batch_g2(const uint64_t *bases, const uint64_t *scalars, const uint64_t *offsets, size_t count, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_batch<Fq2>(bases, scalars, offsets, count, out);
+}
+
 int b200_sum_partials_g1(const uint64_t *pts, size_t n, uint64_t out[12]) { return sum_partials<host::HFq>(pts, n, out); }
 int b200_sum_partials_g2(const uint64_t *pts, size_t n, uint64_t out[24]) { return sum_partials<host::HFq2>(pts, n, out); }
 
@@ -372,6 +384,32 @@ int b200_cppoly_prove_g1(uint64_t key, const uint64_t *v, const uint64_t *r, siz
     std::lock_guard<std::mutex> lk(g_mu);
     return cppoly_prove_g1(key, v, r, d, witness, eval);
 }
+int b200_fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t c1[4], const uint64_t ratio[4], const uint64_t c0[4], size_t n_tail,
+                                const uint64_t *tail)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_scale_inv_geometric(P, n_geo, c1, ratio, c0, n_tail, tail);
+}
+int b200_fr_eq_table(const uint64_t *r, size_t d, uint64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_eq_table(r, d, out);
+}
+int b200_fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_matrix_mle(A, rho, d, v);
+}
+int b200_fr_sumcheck_round(const uint64_t *a, const uint64_t *b, const uint64_t *w, size_t half, uint64_t out[12])
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_sumcheck_round(a, b, w, half, out);
+}
+int b200_fr_sumcheck_rounds(const uint64_t *a, const uint64_t *b, const uint64_t *r, size_t d, uint64_t *h)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_sumcheck_rounds(a, b, r, d, h);
+}
 int b200_fr_fft(uint64_t *a, size_t log_n, int mode, const uint64_t *coset_g)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -455,6 +493,8 @@ int b200_set_tuning_ex(const char *key, int value)
     else if (k == "reduce_split") g_tune_split = value;       // 0 = auto
     else if (k == "use_precomputed") g_tune_pre = value;      // 0: ignore precomputed levels of a key
     else if (k == "host_horner") g_tune_host_horner = value;  // 0: the device also weights and sums the per-job results of a one-window reduction
+    else if (k == "reduce_marginals") g_tune_marginals = value;  // 0: bit decomposition over all segments (round 1)
+    else if (k == "partition_sort") g_tune_sort = value;     // 0: the round-1 global-atomics counting sort
     else if (k == "ones_filter") g_tune_ones = value;         // 0: scalars equal to one go through the sort like any other
     else return fail(B200_ERR_ARG, "unknown tuning key %s", key);
     return B200_OK;

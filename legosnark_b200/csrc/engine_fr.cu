@@ -89,6 +89,204 @@ int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t 
 }
 
 // ------------------------------------------------------------------------------
+// sum-check tables (mle.h / sumcheck.h)
+// ------------------------------------------------------------------------------
+// eq table of d challenges already in D.fr_r -> returned device pointer (D.fr_a or D.fr_b), 2^d entries
+static const Fr *eq_table_device(Device &D, cudaStream_t st, size_t d)
+{
+    const size_t N = (size_t)1 << d;
+    D.fr_a.ensure(N * sizeof(Fr));
+    D.fr_b.ensure(N * sizeof(Fr));
+    Fr *cur = D.fr_a.as<Fr>(), *nxt = D.fr_b.as<Fr>();
+    for (uint32_t j = 0; j < d; j++) {
+        LAUNCH(D, k_fr_eq_step, cdiv((size_t)2 << j, 256), 256, 0, st, (const Fr *)cur, (const Fr *)D.fr_r.as<Fr>(), j, nxt);
+        std::swap(cur, nxt);
+    }
+    return cur;
+}
+
+int fr_eq_table(const uint64_t *r, size_t d, uint64_t *out)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!r || !out) return fail(B200_ERR_ARG, "null argument");
+    if (d < 1 || d > 28) return fail(B200_ERR_ARG, "d out of range (1..28)");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        D.fr_r.ensure(d * sizeof(Fr));
+        CK(cudaMemcpyAsync(D.fr_r.p, r, d * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        const Fr *tbl = eq_table_device(D, st, d);
+        d2h(D, out, tbl, ((size_t)1 << d) * sizeof(Fr), st);
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = (size_t)1 << d;
+        g_stats.kernel_launches = D.launches;
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+int fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!A || !rho || !v) return fail(B200_ERR_ARG, "null argument");
+    if (d < 1 || d > 14) return fail(B200_ERR_ARG, "d out of range (1..14)");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        const size_t n = (size_t)1 << d, N = n * n;
+        D.fr_r.ensure(d * sizeof(Fr));
+        D.fr_w.ensure(N * sizeof(Fr));
+        CK(cudaMemcpyAsync(D.fr_r.p, rho, d * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        h2d(D, D.fr_w.p, A, N * sizeof(Fr), st);
+        const Fr *eq = eq_table_device(D, st, d);
+        // rows split over gridDim.y so that ~4 blocks per SM are in flight
+        const uint32_t bx = cdiv(n, 32);
+        uint32_t ny = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(n / 8), (uint32_t)D.sms * 4 / bx));
+        D.scalars.ensure((size_t)ny * n * sizeof(Fr));
+        D.prefix.ensure(n * sizeof(Fr));
+        LAUNCH(D, k_fr_matrix_mle, dim3(bx, ny), MMLE_THREADS, 0, st, (const Fr *)D.fr_w.as<Fr>(), eq, (uint32_t)d, D.scalars.as<Fr>());
+        LAUNCH(D, k_fr_vec_add_slices, cdiv(n, 256), 256, 0, st, (const Fr *)D.scalars.as<Fr>(), n, ny, D.prefix.as<Fr>());
+        CK(cudaMemcpyAsync(v, D.prefix.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = N;
+        g_stats.kernel_launches = D.launches;
+        g_stats.h2d_bytes = (double)(N + d) * sizeof(Fr);
+        g_stats.d2h_bytes = (double)n * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+static void sumcheck_round_device(Device &D, cudaStream_t st, const Fr *a, const Fr *b, const Fr *w, size_t half, Fr *out3)
+{
+    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(cdiv(half, SC_THREADS), (uint32_t)D.sms * 4));
+    D.coeff.ensure((size_t)blocks * 3 * sizeof(Fr));
+    LAUNCH(D, k_fr_sumcheck_round, blocks, SC_THREADS, 0, st, a, b, w, half, D.coeff.as<Fr>());
+    LAUNCH(D, k_fr_sum3, 1, 96, 0, st, (const Fr *)D.coeff.as<Fr>(), blocks, out3);
+}
+
+int fr_sumcheck_round(const uint64_t *a, const uint64_t *b, const uint64_t *w, size_t half, uint64_t *out)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!a || !b || !out || half == 0) return fail(B200_ERR_ARG, "bad argument");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        D.fr_a.ensure(2 * half * sizeof(Fr));
+        D.fr_b.ensure(2 * half * sizeof(Fr));
+        D.fr_w.ensure(half * sizeof(Fr));
+        D.fr_r.ensure(3 * sizeof(Fr));
+        h2d(D, D.fr_a.p, a, 2 * half * sizeof(Fr), st);
+        h2d(D, D.fr_b.p, b, 2 * half * sizeof(Fr), st);
+        if (w) h2d(D, D.fr_w.p, w, half * sizeof(Fr), st);
+        sumcheck_round_device(D, st, D.fr_a.as<Fr>(), D.fr_b.as<Fr>(), w ? D.fr_w.as<Fr>() : (const Fr *)nullptr, half, D.fr_r.as<Fr>());
+        CK(cudaMemcpyAsync(out, D.fr_r.p, 3 * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = half;
+        g_stats.kernel_launches = D.launches;
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// all d rounds of the sum-check over two tables without a beta factor (CPSumcheckMatrix: DPBetaDummy,
+// sumcheck.h:118-131): round i's three sums, then both tables are bound to r[i] on the device
+// (DPMle::pushRandomness, mle.h:199-210); the tables never return to the host.
+int fr_sumcheck_rounds(const uint64_t *a, const uint64_t *b, const uint64_t *r, size_t d, uint64_t *h)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!a || !b || !r || !h) return fail(B200_ERR_ARG, "null argument");
+    if (d < 1 || d > 28) return fail(B200_ERR_ARG, "d out of range (1..28)");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        const size_t N = (size_t)1 << d;
+        D.fr_a.ensure(N * sizeof(Fr));
+        D.fr_b.ensure(N * sizeof(Fr));
+        D.fr_w.ensure(N * sizeof(Fr));  // ping-pong partners: a in fr_w[0, N/2), b in fr_w[N/2, N)
+        D.fr_r.ensure(d * sizeof(Fr));
+        D.out_norm.ensure(d * 3 * sizeof(Fr));
+        h2d(D, D.fr_a.p, a, N * sizeof(Fr), st);
+        h2d(D, D.fr_b.p, b, N * sizeof(Fr), st);
+        CK(cudaMemcpyAsync(D.fr_r.p, r, d * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        Fr *ca = D.fr_a.as<Fr>(), *cb = D.fr_b.as<Fr>();
+        Fr *na = D.fr_w.as<Fr>(), *nb = D.fr_w.as<Fr>() + N / 2;
+        for (size_t i = 0; i < d; i++) {
+            const size_t half = (size_t)1 << (d - i - 1);
+            sumcheck_round_device(D, st, ca, cb, nullptr, half, D.out_norm.as<Fr>() + 3 * i);
+            if (i + 1 < d) {
+                LAUNCH(D, k_fr_bind_hi, cdiv(half, 256), 256, 0, st, (const Fr *)ca, half, (const Fr *)(D.fr_r.as<Fr>() + i), na);
+                LAUNCH(D, k_fr_bind_hi, cdiv(half, 256), 256, 0, st, (const Fr *)cb, half, (const Fr *)(D.fr_r.as<Fr>() + i), nb);
+                std::swap(ca, na);
+                std::swap(cb, nb);
+            }
+        }
+        CK(cudaMemcpyAsync(h, D.out_norm.p, d * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = N;
+        g_stats.kernel_launches = D.launches;
+        g_stats.h2d_bytes = (double)(2 * N + d) * sizeof(Fr);
+        g_stats.d2h_bytes = (double)d * 3 * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// P[i] *= (c1 ratio^i - c0)^-1 for i < n_geo, then P[n_geo + i] *= tail for i < n_tail (tail may be NULL):
+// step_radix2_domain::divide_by_Z_on_coset (step_radix2_domain.tcc:213-241) with the constants formed by the caller
+int fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t *c1, const uint64_t *ratio, const uint64_t *c0, size_t n_tail,
+                           const uint64_t *tail)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!P || !c1 || !ratio || !c0 || (n_tail && !tail)) return fail(B200_ERR_ARG, "null argument");
+    const size_t n = n_geo + n_tail;
+    if (n == 0) return B200_OK;
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        D.fr_a.ensure(n * sizeof(Fr));
+        D.fr_r.ensure(4 * sizeof(Fr));
+        uint64_t consts[16];
+        memcpy(consts, c1, 32);
+        memcpy(consts + 4, ratio, 32);
+        memcpy(consts + 8, c0, 32);
+        if (tail) memcpy(consts + 12, tail, 32);
+        h2d(D, D.fr_a.p, P, n * sizeof(Fr), st);
+        CK(cudaMemcpyAsync(D.fr_r.p, consts, sizeof consts, cudaMemcpyHostToDevice, st));
+        if (n_geo)
+            LAUNCH(D, k_fr_scale_inv_geometric, cdiv(cdiv(n_geo, INVG_RUN), 128), 128, 0, st, D.fr_a.as<Fr>(), n_geo, (const Fr *)D.fr_r.as<Fr>());
+        if (n_tail) LAUNCH(D, k_fr_scale, cdiv(n_tail, 256), 256, 0, st, D.fr_a.as<Fr>() + n_geo, n_tail, (const Fr *)(D.fr_r.as<Fr>() + 3));
+        d2h(D, P, D.fr_a.p, n * sizeof(Fr), st);
+        CK(cudaStreamSynchronize(st));  // consts lives on this frame
+        g_stats = b200_stats_t{};
+        g_stats.n = n;
+        g_stats.kernel_launches = D.launches;
+        g_stats.h2d_bytes = g_stats.d2h_bytes = (double)n * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// ------------------------------------------------------------------------------
 // radix-2 domains: twiddle tables cached per (device, log n); coset tables per last shift g
 // ------------------------------------------------------------------------------
 struct FrDomain {

@@ -10,6 +10,11 @@
 namespace b200 {
 namespace eng {
 
+// radix-partition bucket sort (engine_sort.cu)
+bool partition_geometry(const MsmGeom &g, size_t n, int sms, SortGeom *out);
+void enqueue_partition_sort(Device &D, cudaStream_t st, const MsmGeom &g, const SortGeom &sg, const uint8_t *d_flags,
+                            const Fr *d_scalars, size_t n);
+
 // ------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------
@@ -52,14 +57,23 @@ inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride
     g.pre_stride = pre_c ? pre_stride : 0;
     g.pre_off = pre_c ? pre_off : 0;
     g.ones = g_tune_ones ? 1 : 0;
-    g.red_jobs = g.red_logS = 0;
+    g.red_jobs = g.red_logS = g.red_hb = g.red_lb = 0;
     g.NB = g.Wb * g.B;
     if (g_tune_L > 0) {
         g.L = (uint32_t)std::min(std::max(g_tune_L, 1), 1023);
     } else {
         const double avg = (double)n * g.W / (double)g.NB;
+        // a precomputed key's top window holds only 254 - (W - 1) c bits: its n digits pile onto the lowest
+        // buckets of the shared set (c = 20: 85 extra entries on 12 388 buckets at 2^20).  A task length that
+        // covers them keeps those buckets whole (no split + combine pass); beyond 512 they are hot buckets anyway.
+        double pile = 0;
+        if (pre_c) {
+            const int top_bits = 254 - (int)((g.W - 1) * g.c);
+            if (top_bits > 0 && top_bits < 31) pile = 1.35 * (double)n / (double)(1u << top_bits);
+            if (avg + pile > 400) pile = 0;
+        }
         uint32_t L = 32;
-        while (L < 2.0 * avg && L < 512) L <<= 1;
+        while (L < std::max(2.0 * avg, avg + pile + 4.0 * std::sqrt(avg + pile)) && L < 512) L <<= 1;
         // k_accumulate runs one thread per task: keep several waves of tasks in flight even when
         // few buckets hold many entries each (a precomputed key with a small window)
         // ... unless the buckets themselves are already that many tasks (one task per bucket needs no combine)
@@ -194,6 +208,13 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     if (g.Wb == 1 && !dense && g_tune_host_horner) {  // one window: per-job sums to the host (MsmGeom::red_jobs)
         P.g.red_jobs = P.njobs;
         P.g.red_logS = P.logS;
+        uint32_t lgM = 0;
+        while ((1u << lgM) < P.M) lgM++;
+        if (g_tune_marginals && lgM >= 2) {  // marginal sums (k_reduce_marginals): 1 + hb + lb points to the host
+            P.g.red_hb = (lgM + 1) / 2;
+            P.g.red_lb = lgM - P.g.red_hb;
+            P.g.red_jobs = 1 + lgM;
+        }
     }
     const uint32_t nres = result_points(P.g);
 
@@ -212,7 +233,7 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.partial.ensure(P.max_tasks * sizeof(XYZZ<F>));
     D.seg_run.ensure(P.nseg * sizeof(XYZZ<F>));
     D.seg_acc.ensure(P.nseg * sizeof(XYZZ<F>));
-    D.job_out.ensure((size_t)g.Wb * (P.njobs + 1) * P.split * sizeof(XYZZ<F>));
+    D.job_out.ensure(std::max((size_t)g.Wb * (P.njobs + 1) * P.split, (size_t)3 << ((P.g.red_hb ? P.g.red_hb : 1))) * sizeof(XYZZ<F>));
     D.split.ensure(std::min<size_t>(g.NB, P.max_tasks) * 4 + 4);
     D.big.ensure(std::min<size_t>(g.NB, P.max_tasks / BIG_TASKS + 1) * 4 + 4);
     if (dense) D.bucket_sum.ensure((size_t)g.NB * sizeof(XYZZ<F>));
@@ -240,9 +261,13 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
                              const Fr *d_scalars, size_t n, bool first_chunk = true)
 {
     const MsmGeom &g = P.g;
-    CK(cudaMemsetAsync(D.cnt.p, 0, (size_t)g.NB * 4, st));
-    CK(cudaMemsetAsync((char *)D.totals.p + 12, 0, 4, st));  // totals[3]: scalars equal to one
-    CK(cudaMemsetAsync(D.len_hist.p, 0, (size_t)(g.L + 1) * 4, st));
+    SortGeom sg;
+    const bool part_sort = g_tune_sort && partition_geometry(g, n, D.sms, &sg);
+    if (!part_sort) {
+        CK(cudaMemsetAsync(D.cnt.p, 0, (size_t)g.NB * 4, st));
+        CK(cudaMemsetAsync((char *)D.totals.p + 12, 0, 4, st));  // totals[3]: scalars equal to one
+        CK(cudaMemsetAsync(D.len_hist.p, 0, (size_t)(g.L + 1) * 4, st));
+    }
 
     uint32_t *cnt = D.cnt.as<uint32_t>(), *off = D.off.as<uint32_t>(), *cursor = D.cursor.as<uint32_t>();
     uint32_t *toff = D.toff.as<uint32_t>(), *totals = D.totals.as<uint32_t>(), *entries = D.entries.as<uint32_t>();
@@ -250,6 +275,11 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
     uint32_t *order = D.order.as<uint32_t>(), *len_hist = D.len_hist.as<uint32_t>(), *len_cursor = D.len_cursor.as<uint32_t>();
     XYZZ<F> *partial = D.partial.as<XYZZ<F>>();
 
+    const size_t max_tasks = (size_t)g.W * n / g.L + g.NB;
+    uint32_t *split = D.split.as<uint32_t>(), *big = D.big.as<uint32_t>();
+    if (part_sort) {
+        enqueue_partition_sort(D, st, g, sg, d_flags, d_scalars, n);
+    } else {
     const uint32_t pblocks = cdiv(n, 256);
     const size_t dstride = (n + 3) & ~(size_t)3;
     LAUNCH(D, k_digit_count, pblocks, 256, 0, st, d_scalars, d_flags, n, dstride, g, cnt, D.digits.as<uint32_t>(),
@@ -258,12 +288,11 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
     LAUNCH(D, k_scan_tiles, 1, 1024, 0, st, tile_sums, P.ntiles, totals);
     LAUNCH(D, k_scan_apply, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
     LAUNCH(D, k_digit_scatter, dim3(cdiv(n, 1024), g.W), 256, 0, st, D.digits.as<uint32_t>(), n, dstride, g, cursor, entries);
-    const size_t max_tasks = (size_t)g.W * n / g.L + g.NB;
     const uint32_t tblocks = cdiv(max_tasks, 256);
-    uint32_t *split = D.split.as<uint32_t>(), *big = D.big.as<uint32_t>();
     LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist, split, big);
     LAUNCH(D, k_len_scan, 1, 1024, 0, st, len_hist, len_cursor, g.L);
     LAUNCH(D, k_task_order, tblocks, 256, 2 * (g.L + 1) * 4, st, meta, totals, g, len_cursor, order);
+    }
     CK(cudaEventRecord(D.ev[2], st));
     LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
     CK(cudaEventRecord(D.ev[3], st));
@@ -298,6 +327,12 @@ void enqueue_reduce(Device &D, cudaStream_t st, const MsmPlan &P, bool dense)
     LAUNCH(D, (k_reduce_segments<F>), cdiv(P.nseg, RED_THREADS), RED_THREADS, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(),
            D.partial.as<XYZZ<F>>(), dense ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr, g, P.logS, seg_run, seg_acc);
     const uint32_t nres = result_points(g);
+    if (g.red_hb) {
+        const uint32_t outs = (2u << g.red_hb) + (1u << g.red_lb);
+        LAUNCH(D, (k_reduce_marginals<F>), outs, MARG_THREADS, 0, st, (const XYZZ<F> *)seg_run, (const XYZZ<F> *)seg_acc,
+               g.red_hb, g.red_lb, D.job_out.as<XYZZ<F>>());
+        LAUNCH(D, (k_reduce_marginal_bits<F>), nres, MARG_THREADS, 0, st, (const XYZZ<F> *)D.job_out.as<XYZZ<F>>(), g.red_hb, g.red_lb, wsums);
+    } else
     LAUNCH(D, (k_reduce_bits<F>), dim3((P.njobs + 1) * P.split, g.Wb), RED2_THREADS, 0, st, seg_run, seg_acc, P.M, P.logS,
            P.split, g.red_jobs ? 1u : 0u, D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
     CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)nres * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
@@ -386,7 +421,26 @@ host::HJac<typename HostOf<F>::type> finalize_windows(const Device &D, const Msm
     static_assert(sizeof(HX) == sizeof(XYZZ<F>), "host/device XYZZ images must match");
     const HX *ws = reinterpret_cast<const HX *>(D.h_pinned);
     J acc = J::inf();
-    if (g.red_jobs) {
+    if (g.red_hb) {
+        // one window, marginal sums: ws[0] = A, ws[1 + b] = T^R_b (b < hb), ws[1 + hb + b] = T^C_b (b < lb);
+        // R = A + 2^logS (2^lb Horner(T^R) + Horner(T^C))
+        const auto at = [&](uint32_t i) { return host::jac_from_xyzz(ws[i].x, ws[i].y, ws[i].zz, ws[i].zzz); };
+        J hr = J::inf(), hc = J::inf();
+        for (int b = (int)g.red_hb - 1; b >= 0; b--) {
+            if (!hr.is_inf()) hr = host::jac_dbl(hr);
+            hr = host::jac_add(hr, at(1 + (uint32_t)b));
+        }
+        if (!hr.is_inf())
+            for (uint32_t i = 0; i < g.red_lb; i++) hr = host::jac_dbl(hr);
+        for (int b = (int)g.red_lb - 1; b >= 0; b--) {
+            if (!hc.is_inf()) hc = host::jac_dbl(hc);
+            hc = host::jac_add(hc, at(1 + g.red_hb + (uint32_t)b));
+        }
+        acc = host::jac_add(hr, hc);
+        if (!acc.is_inf())
+            for (uint32_t i = 0; i < g.red_logS; i++) acc = host::jac_dbl(acc);
+        acc = host::jac_add(acc, at(0));
+    } else if (g.red_jobs) {
         // one window, per-job sums: ws[0] = S_0 = sum_s acc_s, ws[1 + b] = T_b; R = S_0 + 2^logS sum_b 2^b T_b (Horner)
         for (int b = (int)g.red_jobs - 2; b >= 0; b--) {
             if (!acc.is_inf()) acc = host::jac_dbl(acc);
@@ -435,7 +489,7 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         g.NB = g.W * g.B;
         g.Wb = g.W;
         g.pre_stride = g.pre_off = g.ones = 0;
-        g.red_jobs = g.red_logS = 0;
+        g.red_jobs = g.red_logS = g.red_hb = g.red_lb = 0;
         g.L = 0;
         D.scalars.ensure(n * sizeof(Fr));
         D.bases_jac.ensure(n * sizeof(Jacobian<F>));
@@ -502,6 +556,53 @@ int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t 
         const uint32_t *tot = reinterpret_cast<const uint32_t *>((const char *)g_devs[0].h_pinned +
                                                                  (size_t)result_points(geoms[0]) * sizeof(XYZZ<F>));
         fill_stats(g_devs[0], ranges[0].second, geoms[0], tot, std::chrono::duration<double, std::micro>(t1 - t0).count(), h2d, d2h);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    }
+}
+
+// many small MSMs in one call (include/b200_msm.h: b200_msm_batch_*); device 0
+template <class F>
+int msm_batch(const uint64_t *bases, const uint64_t *scalars, const uint64_t *offsets, size_t count, uint64_t *out)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (count == 0) return B200_OK;
+    if (!offsets || !out) return fail(B200_ERR_ARG, "null argument");
+    if (offsets[0] != 0) return fail(B200_ERR_ARG, "offsets[0] must be 0");
+    for (size_t j = 0; j < count; j++)
+        if (offsets[j + 1] < offsets[j]) return fail(B200_ERR_ARG, "offsets must be non-decreasing");
+    const size_t n = offsets[count];
+    if (n && (!bases || !scalars)) return fail(B200_ERR_ARG, "null argument");
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        D.scalars.ensure(std::max<size_t>(n, 1) * sizeof(Fr));
+        D.bases_jac.ensure(std::max<size_t>(n, 1) * sizeof(Jacobian<F>));
+        D.partial.ensure(std::max<size_t>(n, 1) * sizeof(XYZZ<F>));
+        D.off.ensure((count + 1) * 8);
+        D.out_jac.ensure(count * sizeof(Jacobian<F>));
+        D.out_norm.ensure(count * sizeof(Jacobian<F>));
+        if (n) {
+            h2d(D, D.scalars.p, scalars, n * sizeof(Fr), st);
+            h2d(D, D.bases_jac.p, bases, n * sizeof(Jacobian<F>), st);
+        }
+        h2d(D, D.off.p, offsets, (count + 1) * 8, st);
+        if (n)
+            LAUNCH(D, (k_batch_terms<F>), cdiv(n, 64), 64, 0, st, (const Jacobian<F> *)D.bases_jac.as<Jacobian<F>>(),
+                   (const Fr *)D.scalars.as<Fr>(), n, D.partial.as<XYZZ<F>>());
+        LAUNCH(D, (k_batch_sums<F>), cdiv(count, 64), 64, 0, st, (const XYZZ<F> *)D.partial.as<XYZZ<F>>(), (const uint64_t *)D.off.as<uint64_t>(),
+               count, D.out_jac.as<Jacobian<F>>());
+        run_ingest<F, true>(D, st, D.out_jac.as<Jacobian<F>>(), D.out_norm.p, nullptr, count);
+        d2h(D, out, D.out_norm.p, count * sizeof(Jacobian<F>), st);
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = n;
+        g_stats.kernel_launches = D.launches;
+        g_stats.h2d_bytes = (double)n * (sizeof(Fr) + sizeof(Jacobian<F>)) + (double)(count + 1) * 8;
+        g_stats.d2h_bytes = (double)count * sizeof(Jacobian<F>);
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
@@ -643,7 +744,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
                 g.B = SMALL_NBK;
                 g.NB = g.W * g.B;
                 g.pre_stride = g.pre_off = g.ones = 0;
-                g.red_jobs = g.red_logS = 0;
+                g.red_jobs = g.red_logS = g.red_hb = g.red_lb = 0;
                 g.L = 0;
                 D.window_sums.ensure((size_t)g.W * sizeof(XYZZ<F>));
                 D.totals.ensure(32);
@@ -918,6 +1019,7 @@ int test_group_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint32
 
 #define B200_INSTANTIATE_GROUP(F)                                                                                       \
     template int msm_host<F>(const uint64_t *, const uint64_t *, size_t, uint64_t *);                                   \
+    template int msm_batch<F>(const uint64_t *, const uint64_t *, const uint64_t *, size_t, uint64_t *);                \
     template int pin_bases<F>(const uint64_t *, const void *, size_t, uint64_t *);                                      \
     template int msm_pinned<F>(uint64_t, size_t, const uint64_t *, const void *, size_t, void *, uint64_t *);           \
     template int key_precompute<F>(uint64_t, uint32_t);                                                                 \

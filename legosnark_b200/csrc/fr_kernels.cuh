@@ -6,6 +6,9 @@
 //                    level i pairs (2p, 2p+1):  w[p] = t[2p+1] - t[2p],
 //                    t'[p] = -t[2p] (r_i - 1) + t[2p+1] r_i = t[2p] + r_i w[p]
 //   k_fr_bind_hi     DPMle::pushRandomness (LS/prototools/mle.h:199-210): pairs (p, p + half)
+//   k_fr_eq_step     DPBeta::compute_eq_tbl (mle.h:93-105), one level per launch
+//   k_fr_matrix_mle  DPMatrixMle's constructor (mle.h:241-259): matrix rows folded with the eq table
+//   k_fr_sumcheck_round  the sum over p inside CPSumcheck::make_new_h_poly (LS/gadgets/sumcheck.h:85-106)
 //   k_fr_fft_pass    libfqfft's basic radix-2 domain (FQFFT/evaluation_domain/domains/
 //                    basic_radix2_domain_aux.tcc:42-75: bit reversal + log n butterfly stages;
 //                    basic_radix2_domain.tcc: FFT / iFFT / cosetFFT / icosetFFT), several
@@ -85,6 +88,111 @@ static __global__ void __launch_bounds__(256) k_fr_bind_hi(const Fr *__restrict_
 }
 
 // ------------------------------------------------------------------------------
+// sum-check dynamic-programming tables (LS/prototools/mle.h, LS/gadgets/sumcheck.h)
+// ------------------------------------------------------------------------------
+// One level of DPBeta::compute_eq_tbl (mle.h:93-105), restated as written there:
+//     tmp[p] = eqbit(p >= 2^j, r[j]) * dst[p >> 1],   p < 2^(j+1)
+// (level 0 is the same line with dst = {1}).  The reference indexes the previous level by p >> 1, not by the
+// low bits of p; the kernel keeps that indexing, so the table is the reference's table, limb for limb.
+static __global__ void __launch_bounds__(256) k_fr_eq_step(const Fr *__restrict__ src, const Fr *__restrict__ r, uint32_t j,
+                                                           Fr *__restrict__ dst)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ((size_t)2 << j)) return;
+    const Fr rj = r[j];
+    const Fr e = p >= ((size_t)1 << j) ? rj : Fr::sub(Fr::one(), rj);  // eqbit(bool, r), mle.cc:13-16
+    const Fr prev = j == 0 ? Fr::one() : src[p >> 1];
+    dst[p] = Fr::mul(e, prev);
+}
+
+// DPMatrixMle's constructor (mle.h:241-259): v[r] = sum_l A[(l << d) + r] * eq[l], n = 2^d rows l and columns r.
+// Block = 32 columns x 8 row groups: a warp reads 32 consecutive elements of one matrix row (1 KB), the eight
+// partial sums of a column meet in shared memory.  gridDim.y splits the rows further; the y-slices are added by
+// k_fr_vec_add_slices.
+constexpr int MMLE_THREADS = 256;
+static __global__ void __launch_bounds__(MMLE_THREADS) k_fr_matrix_mle(const Fr *__restrict__ A, const Fr *__restrict__ eq, uint32_t d,
+                                                                       Fr *__restrict__ slices)
+{
+    __shared__ Fr sm[MMLE_THREADS];
+    const size_t n = (size_t)1 << d;
+    const uint32_t cl = threadIdx.x & 31u, lg = threadIdx.x >> 5;
+    const size_t r = (size_t)blockIdx.x * 32 + cl;
+    const size_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+    const size_t l0 = (size_t)blockIdx.y * rows_per, l1 = min(n, l0 + rows_per);
+    Fr acc = Fr::zero();
+    if (r < n)
+        for (size_t l = l0 + lg; l < l1; l += 8) acc = Fr::add(acc, Fr::mul(A[(l << d) + r], eq[l]));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (lg == 0 && r < n) {
+#pragma unroll 1
+        for (int g = 1; g < 8; g++) acc = Fr::add(acc, sm[g * 32 + cl]);
+        slices[(size_t)blockIdx.y * n + r] = acc;
+    }
+}
+
+// out[i] = sum_y slices[y * n + i]
+static __global__ void __launch_bounds__(256) k_fr_vec_add_slices(const Fr *__restrict__ slices, size_t n, uint32_t ny, Fr *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr acc = slices[i];
+    for (uint32_t y = 1; y < ny; y++) acc = Fr::add(acc, slices[(size_t)y * n + i]);
+    out[i] = acc;
+}
+
+// The sum inside CPSumcheck::make_new_h_poly (sumcheck.h:85-106) for two committed polynomials:
+//     S(x) = sum_{p < half} w[p] * (a[p] (1 - x) + a[p + half] x) * (b[p] (1 - x) + b[p + half] x)
+// (getMLEPoly, mle.h:218-227: eqbit_poly(0) * v0 + eqbit_poly(1) * v1), w = the beta suffix table of the round or
+// nullptr (DPBetaDummy: the matrix sum-check).  The three coefficients are exact field sums, so any
+// association gives the reference's limbs; the linear factor eqbit_poly(rho[j]) * beta_pre of a real beta is
+// applied by the caller to the three sums.  Block partials -> part[block][3]; k_fr_sum3 adds them.
+constexpr int SC_THREADS = 256;
+static __global__ void __launch_bounds__(SC_THREADS) k_fr_sumcheck_round(const Fr *__restrict__ a, const Fr *__restrict__ b,
+                                                                         const Fr *__restrict__ w, size_t half, Fr *__restrict__ part)
+{
+    __shared__ Fr sm[3][SC_THREADS];
+    Fr c0 = Fr::zero(), c1 = Fr::zero(), c2 = Fr::zero();
+    for (size_t p = (size_t)blockIdx.x * SC_THREADS + threadIdx.x; p < half; p += (size_t)gridDim.x * SC_THREADS) {
+        Fr a0 = a[p], a1 = Fr::sub(a[p + half], a0);
+        const Fr b0 = b[p], b1 = Fr::sub(b[p + half], b0);
+        if (w) {
+            const Fr wp = w[p];
+            a0 = Fr::mul(a0, wp);
+            a1 = Fr::mul(a1, wp);
+        }
+        c0 = Fr::add(c0, Fr::mul(a0, b0));
+        c1 = Fr::add(c1, Fr::mul_add(a0, b1, a1, b0));
+        c2 = Fr::add(c2, Fr::mul(a1, b1));
+    }
+    sm[0][threadIdx.x] = c0;
+    sm[1][threadIdx.x] = c1;
+    sm[2][threadIdx.x] = c2;
+    __syncthreads();
+    for (int o = SC_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int k = 0; k < 3; k++) sm[k][threadIdx.x] = Fr::add(sm[k][threadIdx.x], sm[k][threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) part[(size_t)blockIdx.x * 3 + threadIdx.x] = sm[threadIdx.x][0];
+}
+
+// out[k] = sum_blocks part[block][k], k < 3 (one warp per coefficient)
+static __global__ void __launch_bounds__(96) k_fr_sum3(const Fr *__restrict__ part, uint32_t nblocks, Fr *__restrict__ out)
+{
+    __shared__ Fr sm[96];
+    const uint32_t k = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    Fr acc = Fr::zero();
+    for (uint32_t i = lane; i < nblocks; i += 32) acc = Fr::add(acc, part[(size_t)i * 3 + k]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (lane == 0) {
+        for (int i = 1; i < 32; i++) acc = Fr::add(acc, sm[k * 32 + i]);
+        out[k] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------
 // radix-2 domain
 // ------------------------------------------------------------------------------
 // Fr::root_of_unity (order 2^28) and Fr::multiplicative_generator = 5, Montgomery form
@@ -143,6 +251,44 @@ static __global__ void __launch_bounds__(128) k_fr_pow_table(const Fr *__restric
         out[i0 + t] = cur;
         cur = Fr::mul(cur, b);
     }
+}
+
+// P[i] *= (c1 * ratio^i - c0)^-1, i < n: the per-point divisions of step_radix2_domain::divide_by_Z_on_coset
+// (FQFFT/evaluation_domain/domains/step_radix2_domain.tcc:219-232: one Fp inversion per element on the host there).
+// Thread = run of INVG_RUN consecutive elements: the denominators are formed from ratio^i0 by one product each,
+// inverted together (Montgomery's trick: 3 products per element + one Fermat inversion per run; field_utils.tcc:171-194
+// is the reference's own batch_invert), and applied.  The inverse of a field element is unique: same limbs.
+constexpr int INVG_RUN = 32;
+static __global__ void __launch_bounds__(128) k_fr_scale_inv_geometric(Fr *__restrict__ P, size_t n, const Fr *__restrict__ consts /* c1, ratio, c0 */)
+{
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * INVG_RUN;
+    if (i0 >= n) return;
+    const Fr c1 = consts[0], ratio = consts[1], c0 = consts[2];
+    const uint32_t cnt = (uint32_t)min((size_t)INVG_RUN, n - i0);
+    Fr den[INVG_RUN], pre[INVG_RUN];
+    Fr t = Fr::mul(c1, fr_pow(ratio, i0));  // c1 * ratio^i
+    Fr acc = Fr::one();
+#pragma unroll 1
+    for (uint32_t k = 0; k < cnt; k++) {
+        den[k] = Fr::sub(t, c0);
+        pre[k] = acc;
+        acc = Fr::mul(acc, den[k]);
+        t = Fr::mul(t, ratio);
+    }
+    Fr inv = Fr::inv(acc);
+#pragma unroll 1
+    for (int k = (int)cnt - 1; k >= 0; k--) {
+        const Fr di = Fr::mul(inv, pre[k]);
+        inv = Fr::mul(inv, den[k]);
+        P[i0 + k] = Fr::mul(P[i0 + k], di);
+    }
+}
+
+// P[i] *= s, i < n
+static __global__ void __launch_bounds__(256) k_fr_scale(Fr *__restrict__ P, size_t n, const Fr *__restrict__ s)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) P[i] = Fr::mul(P[i], *s);
 }
 
 constexpr int FFT_THREADS = 256;

@@ -51,6 +51,16 @@ struct MsmGeom {
     // and the host forms S_0 + 2^logS sum_b 2^b T_b (a few dozen cheap host operations instead of a serial chain
     // of doublings and a second combine on a lone warp).  red_jobs == 0: the device returns the window sums.
     uint32_t red_jobs, red_logS;
+    // marginal-sum form of the same (k_reduce_marginals): red_hb + red_lb = log2(segments); the host gets
+    // 1 + red_hb + red_lb points.  red_hb == 0 && red_lb == 0: the bit decomposition over all segments (red_jobs).
+    uint32_t red_hb, red_lb;
+};
+// geometry of the radix-partition sort (sort_kernels.cuh / engine_sort.cu)
+struct SortGeom {
+    uint32_t low_bits;        // buckets per partition = 1 << low_bits
+    uint32_t NP;              // partitions = ceil(NB / 2^low_bits)
+    uint32_t tile;            // scalars per block of k_part_scatter (W * tile <= PART_STAGE_ITEMS)
+    uint32_t hist_per_block;  // scalars per block of k_part_hist (multiple of 256)
 };
 __host__ __device__ __forceinline__ uint32_t result_points(const MsmGeom &g) { return g.red_jobs ? g.red_jobs : g.Wb; }
 __host__ __device__ __forceinline__ uint32_t bucket_base(const MsmGeom &g, uint32_t k) { return g.pre_stride ? 0u : k * g.B; }
@@ -134,25 +144,27 @@ __global__ void __launch_bounds__(128) k_key_level(const Affine<F> *__restrict__
 // ------------------------------------------------------------------------------
 // signed-digit recoding
 // ------------------------------------------------------------------------------
+// The scalar is consumed from the bottom: the window is the low c bits, then the whole 256-bit value moves
+// right by c with eight funnel shifts (static register indices; the round-1 form indexed a limb array with a
+// runtime index, which put it in local memory and cost ~45 instructions per window -- the sort kernels were
+// instruction-bound on it: profiles/r2d ncu capture, sm throughput 78 %).  2 <= c <= 24.
 template <class Fn>
 __device__ __forceinline__ void for_each_window(const Fr &s, uint32_t c, uint32_t W, Fn fn)
 {
-    uint32_t limbs[9];
-#pragma unroll
-    for (int i = 0; i < 8; i++) limbs[i] = s.l[i];
-    limbs[8] = 0;
+    uint32_t l0 = s.l[0], l1 = s.l[1], l2 = s.l[2], l3 = s.l[3], l4 = s.l[4], l5 = s.l[5], l6 = s.l[6], l7 = s.l[7];
     const uint32_t mask = (1u << c) - 1u;
     const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0;
     for (uint32_t k = 0; k < W; k++) {
-        const uint32_t bit = k * c;
-        const uint32_t limb = bit >> 5, sh = bit & 31u;
-        uint32_t raw = 0;
-        if (limb < 8) {
-            const uint64_t two = (uint64_t)limbs[limb] | ((uint64_t)limbs[limb + 1] << 32);
-            raw = (uint32_t)(two >> sh) & mask;
-        }
-        const uint32_t d = raw + carry;
+        const uint32_t d = (l0 & mask) + carry;
+        l0 = __funnelshift_r(l0, l1, c);
+        l1 = __funnelshift_r(l1, l2, c);
+        l2 = __funnelshift_r(l2, l3, c);
+        l3 = __funnelshift_r(l3, l4, c);
+        l4 = __funnelshift_r(l4, l5, c);
+        l5 = __funnelshift_r(l5, l6, c);
+        l6 = __funnelshift_r(l6, l7, c);
+        l7 >>= c;
         uint32_t mag, neg;
         if (d > half) {
             mag = (1u << c) - d;
@@ -685,6 +697,17 @@ constexpr int RED2_THREADS = 128;
 // across the chunks of a pipelined MSM (empty buckets hold infinity); otherwise from the task
 // partials of the single sort.
 template <class F>
+__device__ __forceinline__ XYZZ<F> load_bucket_sum(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
+                                                   const XYZZ<F> *__restrict__ partial, const XYZZ<F> *__restrict__ dense, uint32_t b)
+{
+    if (dense) return dense[b];
+    if (cnt[b]) return partial[toff[b]];
+    return XYZZ<F>::inf();
+}
+
+// The two additions of every step are inlined (the accumulators stay in registers; the out-of-line
+// adder of round 1 kept them in local memory) and the next bucket's sum is loaded while they run.
+template <class F>
 __global__ void __launch_bounds__(RED_THREADS) k_reduce_segments(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ toff,
                                                                   const XYZZ<F> *__restrict__ partial, const XYZZ<F> *__restrict__ dense,
                                                                   MsmGeom g, uint32_t logS, XYZZ<F> *__restrict__ seg_run,
@@ -695,21 +718,35 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_segments(const uint32_t 
     if (seg >= nseg) return;
     const uint32_t b0 = seg << logS;  // segments never straddle windows: S divides B
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-    for (int t = (1 << logS) - 1; t >= 0; t--) {
-        const uint32_t b = b0 + (uint32_t)t;
-        if (dense) {
-            const XYZZ<F> q = dense[b];
-            xyzz_add_cold(&run, &q);
-        } else if (cnt[b]) {
-            const XYZZ<F> q = partial[toff[b]];
-            xyzz_add_cold(&run, &q);
+    int t = (1 << logS) - 1;
+    XYZZ<F> q = load_bucket_sum<F>(cnt, toff, partial, dense, b0 + (uint32_t)t);
+#pragma unroll 1
+    for (; t >= 0; t--) {
+        const XYZZ<F> cur = q;
+        if (t > 0) q = load_bucket_sum<F>(cnt, toff, partial, dense, b0 + (uint32_t)(t - 1));
+        if (sizeof(F) <= 32) {
+            xyzz_add(run, cur);
+            xyzz_add(acc, run);
+        } else {
+            xyzz_add_cold(&run, &cur);
+            xyzz_add_cold(&acc, &run);
         }
-        xyzz_add_cold(&acc, &run);
     }
     seg_run[seg] = run;
     seg_acc[seg] = acc;
 }
 
+// ------------------------------------------------------------------------------
+// level 2 for ONE window of buckets (precomputed keys), by marginal sums.  With M = 2^(hb + lb) segments,
+// s = hi * 2^lb + lo:
+//     sum_s s run_s = 2^lb sum_hi hi R_hi + sum_lo lo C_lo,   R_hi = sum_lo run_(hi,lo),  C_lo = sum_hi run_(hi,lo)
+// k_reduce_marginals: one block per output -- the 2^hb row sums R, the 2^lb column sums C and the 2^hb partial
+//     sums of acc_s (A_hi = sum_lo acc_(hi,lo)): 3 additions per segment instead of ~9 for the bit
+//     decomposition over all M segments;
+// k_reduce_marginal_bits: one block per output -- T^R_b = sum over the hi with bit b set of R_hi, T^C_b likewise,
+//     and A = sum_hi A_hi: 1 + hb + lb points go to the host, which applies the weights (a few dozen host
+//     operations): R = A + 2^logS (2^lb Horner(T^R) + Horner(T^C)).
+// ------------------------------------------------------------------------------
 template <class F>
 __device__ __forceinline__ XYZZ<F> block_sum_point(XYZZ<F> v, XYZZ<F> *sm)
 {
@@ -721,6 +758,73 @@ __device__ __forceinline__ XYZZ<F> block_sum_point(XYZZ<F> v, XYZZ<F> *sm)
         v = warp_sum_point(v, (int)(blockDim.x >> 5));  // blockDim.x / 32 is a power of two
     }
     return v;  // thread 0 holds the block's sum
+}
+
+// one block per output: these sums are chains of dependent point additions (a lone warp needs ~7 us per
+// addition), so every output gets 128 lanes: at most two values per lane, then the 5 + 2 level block tree
+constexpr int MARG_THREADS = 128;
+template <class F>
+__global__ void __launch_bounds__(MARG_THREADS) k_reduce_marginals(const XYZZ<F> *__restrict__ seg_run, const XYZZ<F> *__restrict__ seg_acc,
+                                                                   uint32_t hb, uint32_t lb, XYZZ<F> *__restrict__ marg)
+{
+    __shared__ XYZZ<F> sm[MARG_THREADS / 32];
+    const uint32_t H = 1u << hb, Lo = 1u << lb;
+    const uint32_t w = blockIdx.x;  // 0..H-1: R_hi; H..H+Lo-1: C_lo; then A_hi
+    const XYZZ<F> *src;
+    uint32_t count, stride;
+    if (w < H) {
+        src = seg_run + (size_t)w * Lo;
+        count = Lo;
+        stride = 1;
+    } else if (w < H + Lo) {
+        src = seg_run + (w - H);
+        count = H;
+        stride = Lo;
+    } else {
+        src = seg_acc + (size_t)(w - H - Lo) * Lo;
+        count = Lo;
+        stride = 1;
+    }
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = threadIdx.x; i < count; i += MARG_THREADS) {
+        const XYZZ<F> q = src[(size_t)i * stride];
+        xyzz_add_cold(&acc, &q);
+    }
+    acc = block_sum_point(acc, sm);
+    if (threadIdx.x == 0) marg[w] = acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(MARG_THREADS) k_reduce_marginal_bits(const XYZZ<F> *__restrict__ marg, uint32_t hb, uint32_t lb,
+                                                                       XYZZ<F> *__restrict__ out)
+{
+    __shared__ XYZZ<F> sm[MARG_THREADS / 32];
+    const uint32_t H = 1u << hb, Lo = 1u << lb;
+    const uint32_t job = blockIdx.x;  // 0: A; 1..hb: T^R_b; hb+1..hb+lb: T^C_b
+    const XYZZ<F> *src;
+    uint32_t count, bit = 0;
+    bool all = false;
+    if (job == 0) {
+        src = marg + H + Lo;
+        count = H;
+        all = true;
+    } else if (job <= hb) {
+        src = marg;
+        count = H >> 1;
+        bit = job - 1;
+    } else {
+        src = marg + H;
+        count = Lo >> 1;
+        bit = job - 1 - hb;
+    }
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = threadIdx.x; i < count; i += MARG_THREADS) {
+        const uint32_t s0 = all ? i : (((i >> bit) << (bit + 1)) | (1u << bit) | (i & ((1u << bit) - 1u)));
+        const XYZZ<F> q = src[s0];
+        xyzz_add_cold(&acc, &q);
+    }
+    acc = block_sum_point(acc, sm);
+    if (threadIdx.x == 0) out[job] = acc;
 }
 
 // Sum of the bases whose scalar is one (list built by k_digit_count).  Every thread adds its strided
@@ -959,6 +1063,53 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const BaseT *__rest
         v = warp_sum_point(v, (int)SMALL_NBK);
         if (lane == 0) window_sums[k] = v;
     }
+}
+
+// ------------------------------------------------------------------------------
+// batched tiny MSMs (b200_msm_batch_*: the per-column multi_exp calls of mtxmultiexp, LS/gadgets/subspace.cc:18-25).
+// k_batch_terms: one thread per term, s_i * P_i by a fixed 4-bit window (15 table additions, then 4 doublings + at
+// most one addition per window; the table lives in local memory, the chain is latency-bound and all terms run
+// side by side).  k_batch_sums: one thread per MSM adds its terms.
+// ------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(64) k_batch_terms(const Jacobian<F> *__restrict__ bases, const Fr *__restrict__ scalars_mont, size_t n,
+                                                     XYZZ<F> *__restrict__ term_out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Jacobian<F> p = bases[i];
+    XYZZ<F> r = XYZZ<F>::inf();
+    if (!p.z.is_zero()) {
+        const Fr s = Fr::from_mont(scalars_mont[i]);
+        XYZZ<F> tab[15];  // tab[d - 1] = d * P
+        tab[0] = XYZZ<F>::from_jacobian(p);
+        for (int d = 1; d < 15; d++) {
+            tab[d] = tab[d - 1];
+            xyzz_add_cold(&tab[d], &tab[0]);
+        }
+#pragma unroll 1
+        for (int w = 63; w >= 0; w--) {
+            if (!r.is_inf())
+                for (int t = 0; t < 4; t++) xyzz_dbl_cold(&r);
+            const uint32_t d = (s.l[w >> 3] >> ((w & 7) * 4)) & 15u;
+            if (d) xyzz_add_cold(&r, &tab[d - 1]);
+        }
+    }
+    term_out[i] = r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(64) k_batch_sums(const XYZZ<F> *__restrict__ term, const uint64_t *__restrict__ offsets, size_t count,
+                                                    Jacobian<F> *__restrict__ out)
+{
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint64_t i = offsets[j]; i < offsets[j + 1]; i++) {
+        const XYZZ<F> q = term[i];
+        xyzz_add_cold(&acc, &q);
+    }
+    out[j] = acc.to_jacobian();
 }
 
 // ------------------------------------------------------------------------------

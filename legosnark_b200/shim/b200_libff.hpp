@@ -121,6 +121,26 @@ inline T msm(const T *bases, const FieldT *scalars, size_t n)
     return point_from_limbs<T>(out);
 }
 
+// out[j] = sum over [offsets[j], offsets[j+1]) of scalars[i] * bases[i]: many small MSMs submitted together
+// (b200_msm_batch_*).  The caller of LegoSNARK's mtxmultiexp is bound to it by shim/sparsemexp.h.
+template <typename T, typename FieldT>
+inline std::vector<T> msm_batch(const std::vector<T> &bases, const std::vector<FieldT> &scalars, const std::vector<uint64_t> &offsets)
+{
+    static_assert(std::is_same<FieldT, typename T::scalar_field>::value && sizeof(FieldT) == 32, "scalars must be the group's Fr");
+    if (offsets.empty() || offsets.back() != bases.size() || bases.size() != scalars.size())
+        throw std::runtime_error("msm_batch: bases, scalars and offsets disagree");
+    ensure_init();
+    const size_t L = group_traits<T>::limbs, count = offsets.size() - 1;
+    std::vector<uint64_t> out(count * L);
+    const uint64_t *b = bases.empty() ? nullptr : limbs_of(bases.data());
+    const uint64_t *s = scalars.empty() ? nullptr : reinterpret_cast<const uint64_t *>(scalars.data());
+    check(group_traits<T>::group == 0 ? b200_msm_batch_g1(b, s, offsets.data(), count, out.data())
+                                      : b200_msm_batch_g2(b, s, offsets.data(), count, out.data()), "b200_msm_batch");
+    std::vector<T> res(count, T::zero());
+    for (size_t j = 0; j < count; j++) res[j] = point_from_limbs<T>(out.data() + j * L);
+    return res;
+}
+
 // (sum s_i g_i, sum s_i h_i) for g_i in a G2 group and h_i in a G1 group over one scalar vector:
 // the MSM behind libsnark's knowledge_commitment<T1,T2> (kc_multiexp.tcc:21-89).
 template <typename T1, typename T2, typename FieldT>

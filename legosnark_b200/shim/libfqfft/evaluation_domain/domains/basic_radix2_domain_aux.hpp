@@ -28,6 +28,8 @@
 
 #include <libff/algebra/fields/field_utils.hpp>
 
+#include <cstdlib>
+
 #include "b200_msm.h"
 
 namespace libfqfft {
@@ -51,7 +53,8 @@ inline bool is_bn254_fr()
 inline void ensure_engine()
 {
     static const bool once = [] {
-        if (b200_device_count() == 0 && b200_init(0) != B200_OK)
+        const char *e = std::getenv("B200_GPUS");  // same rule as b200shim::ensure_init: whichever shim runs first, B200_GPUS holds
+        if (b200_device_count() == 0 && b200_init(e ? std::atoi(e) : 0) != B200_OK)
             throw std::runtime_error(std::string("b200_init failed: ") + b200_last_error());
         return true;
     }();

@@ -1,0 +1,43 @@
+// Shadow of libfqfft's step_radix2_domain.hpp: the reference's class as it is (included next on the path), plus an
+// explicit specialisation of divide_by_Z_on_coset for BN254's Fr.  The reference divides by the vanishing polynomial
+// with one Fp inversion PER POINT of the big half (step_radix2_domain.tcc:213-241: `P[i] *= (... * elt - ...).inverse()`
+// for i < big_m, serial, ~3 us each through mpn_gcdext): 6 s of the 6.9 s Groth16 prover of the 128 x 128 matrix product
+// (2^21 + 1 constraints -> this domain), BASELINE.json configs[3].  Here the host forms the four constants exactly as
+// the reference does and the device inverts the denominators in batches (b200_fr_scale_inv_geometric).
+// The transforms of this domain already reach the engine through _basic_radix2_FFT (basic_radix2_domain_aux.hpp).
+#ifndef B200_SHIM_STEP_RADIX2_DOMAIN_HPP_
+#define B200_SHIM_STEP_RADIX2_DOMAIN_HPP_
+
+#include_next <libfqfft/evaluation_domain/domains/step_radix2_domain.hpp>
+
+#if defined(CURVE_BN128) || defined(CURVE_ALT_BN128)
+#include <libff/common/default_types/ec_pp.hpp>
+#include <libfqfft/evaluation_domain/domains/basic_radix2_domain_aux.hpp>
+
+namespace libfqfft {
+
+template <>
+inline void step_radix2_domain<libff::Fr<libff::default_ec_pp>>::divide_by_Z_on_coset(std::vector<libff::Fr<libff::default_ec_pp>> &P)
+{
+    typedef libff::Fr<libff::default_ec_pp> FieldT;
+    static_assert(sizeof(FieldT) == 32, "unexpected scalar layout");
+    if (P.size() < big_m + small_m) throw DomainSizeException("step_radix2: divide_by_Z_on_coset expects the whole coset");
+    // the constants of step_radix2_domain.tcc:216-222 and :236-237
+    const FieldT coset = FieldT::multiplicative_generator;
+    const FieldT Z0 = (coset ^ big_m) - FieldT::one();
+    const FieldT c1 = (coset ^ small_m) * Z0;
+    const FieldT c0 = (omega ^ small_m) * Z0;
+    const FieldT ratio = omega ^ (2 * small_m);
+    const FieldT Z1 = ((((coset * omega) ^ big_m) - FieldT::one()) * (((coset * omega) ^ small_m) - (omega ^ small_m)));
+    const FieldT Z1_inverse = Z1.inverse();
+    b200_detail::ensure_engine();
+    if (b200_fr_scale_inv_geometric(reinterpret_cast<uint64_t *>(P.data()), big_m, reinterpret_cast<const uint64_t *>(&c1),
+                                    reinterpret_cast<const uint64_t *>(&ratio), reinterpret_cast<const uint64_t *>(&c0), small_m,
+                                    reinterpret_cast<const uint64_t *>(&Z1_inverse)) != B200_OK)
+        throw std::runtime_error(std::string("b200_fr_scale_inv_geometric failed: ") + b200_last_error());
+}
+
+}  // namespace libfqfft
+#endif  // BN254 default curve
+
+#endif  // B200_SHIM_STEP_RADIX2_DOMAIN_HPP_

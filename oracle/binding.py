@@ -259,6 +259,70 @@ class Checker:
         self._lscall("fr_mle_bind", _ptr(table), ctypes.c_size_t(half), _ptr(r), _ptr(out))
         return out
 
+    # -- sum-check tables (LS/prototools/mle.h, LS/gadgets/sumcheck.h) --------------------
+    def fr_eq_table(self, r):
+        r = _c(r, 4)
+        d = r.shape[0]
+        out = np.zeros((1 << d, 4), dtype=np.uint64)
+        self._lscall("fr_eq_table", _ptr(r), ctypes.c_size_t(d), _ptr(out))
+        return out
+
+    def fr_matrix_mle(self, A, rho):
+        A, rho = _c(A, 4), _c(rho, 4)
+        d = rho.shape[0]
+        assert A.shape[0] == 1 << (2 * d)
+        out = np.zeros((1 << d, 4), dtype=np.uint64)
+        self._lscall("fr_matrix_mle", _ptr(A), _ptr(rho), ctypes.c_size_t(d), _ptr(out))
+        return out
+
+    def fr_sumcheck_round(self, a, b, w=None):
+        """restatement only: (3, 4) coefficients of sum_p w[p] * mle_a_poly(p) * mle_b_poly(p)"""
+        assert self.kind == "orc"
+        a, b = _c(a, 4), _c(b, 4)
+        half = a.shape[0] // 2
+        w = None if w is None else _c(w, 4)
+        out = np.zeros((3, 4), dtype=np.uint64)
+        self._lscall("fr_sumcheck_round", _ptr(a), _ptr(b), _ptr(w), ctypes.c_size_t(half), _ptr(out))
+        return out
+
+    def fr_sumcheck_rounds(self, a, b, r):
+        """(d, 3, 4): the beta-less round polynomials.  ref: CPSumcheck::make_new_h_poly with DPBetaDummy."""
+        a, b, r = _c(a, 4), _c(b, 4), _c(r, 4)
+        d = r.shape[0]
+        assert a.shape[0] == 1 << d
+        if self.kind == "orc":
+            out = np.zeros((d, 3, 4), dtype=np.uint64)
+            self._lscall("fr_sumcheck_rounds", _ptr(a), _ptr(b), _ptr(r), ctypes.c_size_t(d), _ptr(out))
+            return out
+        h, nc = self.sumcheck_h_polys(a, b, None, r)
+        assert nc == 3
+        return h[:, :3]
+
+    def sumcheck_h_polys(self, a, b, rho, r):
+        """reference only: h[i] of every round through CPSumcheck::make_new_h_poly, with DPBeta(rho) or, for
+        rho = None, DPBetaDummy; returns ((d, 4, 4) coefficients, coefficients per polynomial)."""
+        assert self.kind == "ref"
+        a, b, r = _c(a, 4), _c(b, 4), _c(r, 4)
+        d = r.shape[0]
+        rho = None if rho is None else _c(rho, 4)
+        out = np.zeros((d, 4, 4), dtype=np.uint64)
+        nc = ctypes.c_size_t(0)
+        rc = self._ls().ref_sumcheck_h_polys(_ptr(a), _ptr(b), _ptr(rho), _ptr(r), ctypes.c_size_t(d), ctypes.c_size_t(4), _ptr(out),
+                                             ctypes.byref(nc))
+        if rc != 0:
+            raise RuntimeError("ref_sumcheck_h_polys failed")
+        return out, int(nc.value)
+
+    def fr_beta_suffix(self, rho):
+        """reference only: DPBeta(d, rho).beta_suff_rho_cur[0 .. 2^(d-1)) after construction (the round-0 suffix values)"""
+        assert self.kind == "ref"
+        rho = _c(rho, 4)
+        d = rho.shape[0]
+        out = np.zeros((1 << (d - 1), 4), dtype=np.uint64)
+        if self._ls().ref_fr_beta_suffix(_ptr(rho), ctypes.c_size_t(d), _ptr(out)) != 0:
+            raise RuntimeError("ref_fr_beta_suffix failed")
+        return out
+
     def fr_fft(self, a, mode=0, g=None):
         a = _c(a, 4).copy()
         log_n = int(a.shape[0]).bit_length() - 1

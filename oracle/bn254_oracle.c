@@ -584,6 +584,107 @@ int orc_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint6
     return 0;
 }
 
+/* DPBeta::compute_eq_tbl: LS/prototools/mle.h:93-105, level by level as written (tmp[p] = eqbit(msb, r[j]) * dst[p >> 1]);
+ * eqbit(bool, r): LS/prototools/mle.cc:13-16 */
+int orc_fr_eq_table(const uint64_t *r, size_t d, uint64_t *out)
+{
+    const size_t N = (size_t)1 << d;
+    const fp_t *rr = (const fp_t *)r;
+    fp_t *dst = (fp_t *)malloc(N * sizeof(fp_t)), *tmp = (fp_t *)malloc(N * sizeof(fp_t));
+    if (!dst || !tmp || d == 0) return 1;
+    fr_sub(&dst[0], &FR.one, &rr[0]);
+    dst[1] = rr[0];
+    for (size_t j = 1; j < d; j++) {
+        fp_t one_minus;
+        fr_sub(&one_minus, &FR.one, &rr[j]);
+        for (size_t p = 0; p < ((size_t)1 << (j + 1)); p++) {
+            const int msb = p >= ((size_t)1 << j);
+            fr_mul(&tmp[p], msb ? &rr[j] : &one_minus, &dst[p >> 1]);
+        }
+        fp_t *sw = tmp;
+        tmp = dst;
+        dst = sw;
+    }
+    memcpy(out, dst, N * sizeof(fp_t));
+    free(dst);
+    free(tmp);
+    return 0;
+}
+
+/* DPMatrixMle::DPMatrixMle: LS/prototools/mle.h:241-259: v[r] = sum_l A[(l << d) + r] * eqTbl[l] */
+int orc_fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v)
+{
+    const size_t n = (size_t)1 << d;
+    const fp_t *AA = (const fp_t *)A;
+    fp_t *eq = (fp_t *)malloc(n * sizeof(fp_t)), *vv = (fp_t *)v;
+    if (!eq || orc_fr_eq_table(rho, d, (uint64_t *)eq)) return 1;
+    memset(vv, 0, n * sizeof(fp_t));
+    for (size_t rr = 0; rr < n; rr++)
+        for (size_t l = 0; l < n; l++) {
+            fp_t inc;
+            fr_mul(&inc, &AA[(l << d) + rr], &eq[l]);
+            fr_add(&vv[rr], &vv[rr], &inc);
+        }
+    free(eq);
+    return 0;
+}
+
+/* The sum of CPSumcheck::make_new_h_poly (LS/gadgets/sumcheck.h:85-106) over two DPMle tables (getMLEPoly, mle.h:218-227:
+ * eqbit_poly(0) * v0 + eqbit_poly(1) * v1 = v0 + (v1 - v0) x), polynomial products as PolyT::mul (polytools.h:54-64), with an
+ * optional per-p scalar w[p] (the beta suffix; NULL = DPBetaDummy).  out = 3 coefficients. */
+int orc_fr_sumcheck_round(const uint64_t *a, const uint64_t *b, const uint64_t *w, size_t half, uint64_t *out)
+{
+    const fp_t *aa = (const fp_t *)a, *bb = (const fp_t *)b, *ww = (const fp_t *)w;
+    fp_t c[3], minus_one;
+    memset(c, 0, sizeof c);
+    fr_sub(&minus_one, &c[0], &FR.one);
+    for (size_t p = 0; p < half; p++) {
+        fp_t pa[2], pb[2], t, prod[3];
+        /* mle poly: (1, -1) * v0 + (0, 1) * v1 */
+        pa[0] = aa[p];
+        fr_mul(&t, &minus_one, &aa[p]);
+        fr_add(&pa[1], &t, &aa[p + half]);
+        pb[0] = bb[p];
+        fr_mul(&t, &minus_one, &bb[p]);
+        fr_add(&pb[1], &t, &bb[p + half]);
+        if (ww) {
+            fr_mul(&pa[0], &pa[0], &ww[p]);
+            fr_mul(&pa[1], &pa[1], &ww[p]);
+        }
+        memset(prod, 0, sizeof prod);
+        for (int i = 0; i < 2; i++)
+            for (int j = 0; j < 2; j++) {
+                fr_mul(&t, &pa[i], &pb[j]);
+                fr_add(&prod[i + j], &prod[i + j], &t);
+            }
+        for (int k = 0; k < 3; k++) fr_add(&c[k], &c[k], &prod[k]);
+    }
+    memcpy(out, c, sizeof c);
+    return 0;
+}
+
+/* the round loop of CPSumcheck::prove (LS/gadgets/sumcheck.cc:56-70) without a beta factor: h[i], then pushRandomness(r[i]) */
+int orc_fr_sumcheck_rounds(const uint64_t *a, const uint64_t *b, const uint64_t *r, size_t d, uint64_t *h)
+{
+    const size_t N = (size_t)1 << d;
+    uint64_t *ca = (uint64_t *)malloc(N * 32), *cb = (uint64_t *)malloc(N * 32), *na = (uint64_t *)malloc(N * 32), *nb = (uint64_t *)malloc(N * 32);
+    if (!ca || !cb || !na || !nb) return 1;
+    memcpy(ca, a, N * 32);
+    memcpy(cb, b, N * 32);
+    for (size_t i = 0; i < d; i++) {
+        const size_t half = (size_t)1 << (d - i - 1);
+        orc_fr_sumcheck_round(ca, cb, NULL, half, h + 12 * i);
+        if (i + 1 < d) {
+            orc_fr_mle_bind(ca, half, r + 4 * i, na);
+            orc_fr_mle_bind(cb, half, r + 4 * i, nb);
+            uint64_t *t = ca; ca = na; na = t;
+            t = cb; cb = nb; nb = t;
+        }
+    }
+    free(ca); free(cb); free(na); free(nb);
+    return 0;
+}
+
 /* Fr::root_of_unity, Fr::s = 28 (alt_bn128_init.cpp:57-60); get_root_of_unity: field_utils.tcc:38-51 */
 static void fr_root_of_unity(fp_t *omega, size_t logn)
 {

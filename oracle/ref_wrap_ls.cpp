@@ -5,6 +5,11 @@
 //   ref_fr_eval_mle       MultiVPolyT::evalMLE          (src/prototools/polytools.h:207-234)
 //   ref_fr_mle_bind       DPMle::pushRandomness         (src/prototools/mle.h:199-210)
 //   ref_cppoly_prove_g1   CPPoly::prove                 (src/gadgets/poly.h:45-91) over an installed key
+//   ref_fr_eq_table       DPBeta::compute_eq_tbl        (src/prototools/mle.h:93-105)
+//   ref_fr_matrix_mle     DPMatrixMle::DPMatrixMle      (src/prototools/mle.h:241-259)
+//   ref_sumcheck_h_polys  the round loop of CPSumcheck::prove (src/gadgets/sumcheck.cc:56-70): make_new_h_poly
+//                         (src/gadgets/sumcheck.h:85-106) + pushRandomness, with DPBeta or DPBetaDummy
+//   ref_fr_beta_suffix    DPBeta's suffix table after precomputeAll (src/prototools/mle.h:130-150)
 //   ref_fr_fft            libfqfft basic_radix2_domain  (libfqfft/evaluation_domain/domains/basic_radix2_domain.tcc)
 // LegoSNARK compiles with CURVE=BN128 only: LFr = bn128 Fr, same Montgomery limbs as
 // alt_bn128's.
@@ -15,6 +20,7 @@ using namespace std;
 
 #include "poly.h"
 #include "mle.h"
+#include "sumcheck.h"
 #include <libfqfft/evaluation_domain/domains/basic_radix2_domain.hpp>
 
 namespace {
@@ -62,6 +68,60 @@ int ref_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint6
     DPMle mle(d, 2 * half, load_fr(table, 2 * half));
     mle.pushRandomness(load_fr(r, 1)[0], 0);
     for (size_t p = 0; p < half; p++) store_fr(out + 4 * p, mle.getVTable(0, p));
+    return 0;
+}
+
+int ref_fr_eq_table(const uint64_t *r, size_t d, uint64_t *out)
+{
+    init_once();
+    const size_t N = (size_t)1 << d;
+    Ins dst(N), tmp(N);
+    DPBeta::compute_eq_tbl(d, dst, tmp, load_fr(r, d));
+    for (size_t p = 0; p < N; p++) store_fr(out + 4 * p, dst[p]);
+    return 0;
+}
+
+int ref_fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v)
+{
+    init_once();
+    const size_t n = (size_t)1 << d;
+    DPMatrixMle m(d, n, load_fr(A, n * n), load_fr(rho, d));
+    const Ins vv = m.getV();
+    for (size_t p = 0; p < n; p++) store_fr(v + 4 * p, vv[p]);
+    return 0;
+}
+
+int ref_fr_beta_suffix(const uint64_t *rho, size_t d, uint64_t *out)
+{
+    init_once();
+    DPBeta beta(d, load_fr(rho, d));
+    for (size_t p = 0; p < ((size_t)1 << (d - 1)); p++) store_fr(out + 4 * p, beta.beta_suff_rho_cur[p]);
+    return 0;
+}
+
+// h[i] for every round i < d (coefficients, low degree first, `stride` slots of 4 limbs per round; *ncoef = coefficients per
+// polynomial: 3 without beta, 4 with); rho == nullptr selects DPBetaDummy (CPSumcheckMatrix::init_beta, sumcheck.h:118-121)
+int ref_sumcheck_h_polys(const uint64_t *a, const uint64_t *b, const uint64_t *rho, const uint64_t *r, size_t d, size_t stride,
+                         uint64_t *out, size_t *ncoef)
+{
+    init_once();
+    const size_t N = (size_t)1 << d;
+    CPSumcheck sc(nullptr, nullptr);
+    shared_ptr<DPBeta> beta = rho ? make_shared<DPBeta>(d, load_fr(rho, d)) : shared_ptr<DPBeta>(make_shared<DPBetaDummy>());
+    vector<shared_ptr<DPMle>> mles;
+    mles.push_back(make_shared<DPMle>(d, N, load_fr(a, N)));
+    mles.push_back(make_shared<DPMle>(d, N, load_fr(b, N)));
+    const vector<LFr> rr = load_fr(r, d);
+    for (size_t i = 0; i < d; i++) {
+        const PolyT h = sc.make_new_h_poly(d, i, beta, mles);
+        if (h.vRepr.size() > stride) return 1;
+        *ncoef = h.vRepr.size();
+        for (size_t k = 0; k < h.vRepr.size(); k++) store_fr(out + 4 * (i * stride + k), h.vRepr[k]);
+        if (i + 1 < d) {
+            beta->pushRandomness(rr[i], i);
+            for (auto &m : mles) m->pushRandomness(rr[i], i);
+        }
+    }
     return 0;
 }
 

@@ -313,6 +313,33 @@ def test_precomputed_window_22(engine, orc, grp, log2n):
         key.close()
 
 
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_batched_small_msms(engine, orc, grp):
+    """b200_msm_batch_*: the per-column MSMs of mtxmultiexp (LS/gadgets/subspace.cc:18-25; cplink's keygen issues 2 050
+    columns of one or two terms, LS/utils/sparsemexp.h:62-90) in one call.  Columns of 0, 1, 2 and a few dozen terms,
+    zero bases, zero / one scalars (sparsemexpG's special cases), repeated and opposite bases, raw Jacobian inputs;
+    every column against the oracle's multi_exp."""
+    rng = np.random.default_rng(9)
+    sizes = [0, 1, 2, 2, 1, 0, 3, 40, 2, 1] + [int(x) for x in rng.integers(1, 3, size=60 if grp == "g1" else 20)]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    n = int(offsets[-1])
+    P, _ = inputs.bases(orc, grp, n, seed=701, affine=False)
+    s = inputs.fr_uniform(orc, n, seed=702)
+    one = ints_to_mont([1], R_ORDER)[0]
+    P[3] = inputs.zero_point(grp)
+    s[4] = 0
+    s[5] = one
+    P[11] = P[10]                                  # column 7 holds a repeated base ...
+    P[13] = inputs.negate(orc, grp, P[12:13])[0]   # ... and an opposite pair
+    s[13] = s[12]
+    got = engine.multi_exp_batch(grp, P, s, offsets)
+    assert got.shape == (len(sizes), P.shape[1])
+    for j in range(len(sizes)):
+        lo, hi = int(offsets[j]), int(offsets[j + 1])
+        assert (got[j] == orc.msm(grp, P[lo:hi], s[lo:hi], variant=1)).all(), (grp, j, sizes[j])
+    assert engine.multi_exp_batch(grp, P[:0], s[:0], np.zeros(1, dtype=np.uint64)).shape == (0, P.shape[1])
+
+
 @pytest.mark.parametrize("n", [0, 1, 65, 1026, 6000])
 def test_knowledge_commitment_pair(engine, orc, n):
     """knowledge_commitment<G2,G1> MSM (SNK/knowledge_commitment/kc_multiexp.tcc:21-89: the B query
