@@ -339,6 +339,20 @@ def mle_push_randomness(table, r):
     return out
 
 
+def scale_inv_geometric(P, n_geo, c1, ratio, c0, tail=None):
+    """P[i] *= (c1 * ratio^i - c0)^-1 for i < n_geo and P[n_geo + i] *= tail: the divisions of libfqfft's
+    step_radix2_domain::divide_by_Z_on_coset (step_radix2_domain.tcc:213-241) with caller-formed constants."""
+    P = _arr(P, 4).copy()
+    n_tail = P.shape[0] - n_geo
+    if n_tail < 0 or (n_tail and tail is None):
+        raise ValueError("bad sizes")
+    c1, ratio, c0 = _arr(c1, 4), _arr(ratio, 4), _arr(c0, 4)
+    tail = None if tail is None else _arr(tail, 4)
+    _check(lib().b200_fr_scale_inv_geometric(_p(P), _sz(n_geo), _p(c1), _p(ratio), _p(c0), _sz(n_tail), _p(tail)),
+           "b200_fr_scale_inv_geometric")
+    return P
+
+
 def compute_eq_tbl(r):
     """DPBeta::compute_eq_tbl (LS/prototools/mle.h:93-105): the 2^d-entry table, level by level as the reference writes it."""
     r = _arr(r, 4)

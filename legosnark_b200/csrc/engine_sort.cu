@@ -11,7 +11,7 @@ bool partition_geometry(const MsmGeom &g, size_t n, int sms, SortGeom *out)
 {
     uint32_t lg = 0;
     while (((uint64_t)1 << lg) < g.NB) lg++;
-    uint32_t low = lg > 10 ? lg - 10 : 0;  // ~1024 partitions
+    uint32_t low = lg > 11 ? lg - 11 : 0;  // ~2048 partitions
     if (low > PART_MAX_LOW) low = PART_MAX_LOW;
     const uint64_t NP = ((uint64_t)g.NB + ((1u << low) - 1)) >> low;
     if (NP > PART_MAX_NP || g.W > PART_STAGE_ITEMS / 32 || g.L + 1 > 2048) return false;

@@ -35,11 +35,11 @@ namespace b200 {
 
 constexpr uint32_t PART_MAX_NP = 4096;         // partitions (shared histogram of the MSD pass)
 constexpr uint32_t PART_MAX_LOW = 12;          // at most 4096 buckets per partition (shared counters of the LSD pass)
-constexpr uint32_t PART_STAGE_ITEMS = 12288;   // (entry, bucket) pairs staged per block of the MSD pass: 96 KB
-constexpr uint32_t FINE_STAGE = 16384;         // entries staged per block of the LSD pass: 64 KB
+constexpr uint32_t PART_STAGE_ITEMS = 11264;   // (entry, bucket) pairs staged per block of the MSD pass: 88 KB (two blocks per SM with 2048 partitions)
+constexpr uint32_t FINE_STAGE = 10240;         // entries staged per block of the LSD pass: 40 KB (five blocks per SM)
 constexpr uint32_t PART_THREADS = 256;           // k_part_hist
 constexpr uint32_t SCAT_THREADS = 1024;          // k_part_scatter: one scalar per thread, two blocks per SM
-constexpr uint32_t FINE_THREADS = 512;
+constexpr uint32_t FINE_THREADS = 384;          // 5 x 384 threads per SM: 2048 partitions run in 2.8 waves (ncu: r2e had 2.3 waves at 3 x 512)
 
 __host__ __device__ __forceinline__ uint32_t part_npad(uint32_t NP) { return (NP + 1u) & ~1u; }
 inline size_t part_scatter_smem(const SortGeom &sg) { return (size_t)part_npad(sg.NP) * 3 * 4 + (size_t)PART_STAGE_ITEMS * 8; }

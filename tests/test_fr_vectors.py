@@ -167,6 +167,27 @@ def test_gpu_cppoly_prove(engine, orc, golden):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_geo,n_tail", [(1, 0), (31, 1), (32, 0), (33, 2), (4096 + 7, 1), (1 << 16, 1)])
+def test_gpu_scale_inv_geometric(engine, orc, n_geo, n_tail):
+    """b200_fr_scale_inv_geometric = the divisions of step_radix2_domain::divide_by_Z_on_coset
+    (step_radix2_domain.tcc:213-241): P[i] * (c1 ratio^i - c0)^-1, checked with Python integers (the inverse of a
+    field element is unique); run lengths on both sides of the per-thread batch of 32."""
+    from oracle.binding import mont_to_ints
+    n = n_geo + n_tail
+    P = orc.sha512_rng_fr(2100 + n_geo, n)
+    c = orc.sha512_rng_fr(2200 + n_geo, 4)
+    got = engine.scale_inv_geometric(P, n_geo, c[0], c[1], c[2], c[3] if n_tail else None)
+    Pi, (c1, ratio, c0, tail) = mont_to_ints(P, R_ORDER), mont_to_ints(c, R_ORDER)
+    want, t = [], c1
+    for i in range(n_geo):
+        want.append(Pi[i] * pow((t - c0) % R_ORDER, -1, R_ORDER) % R_ORDER)
+        t = t * ratio % R_ORDER
+    for i in range(n_tail):
+        want.append(Pi[n_geo + i] * tail % R_ORDER)
+    assert (got == ints_to_mont(want, R_ORDER)).all()
+
+
+@pytest.mark.gpu
 def test_gpu_fr_argument_errors(engine):
     import legosnark_b200 as lb
     a = np.zeros((8, 4), dtype=np.uint64)
