@@ -180,6 +180,12 @@ int b200_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_
 int b200_fr_eval_mle(const uint64_t *v /* 2^d x 4 */, const uint64_t *r /* d x 4 */, size_t d, uint64_t out[4]);
 /* DPMle::pushRandomness (LS/prototools/mle.h:199-210): out[p] = table[p] (1 - r) + table[p + half] r. */
 int b200_fr_mle_bind(const uint64_t *table /* 2 half x 4 */, size_t half, const uint64_t r[4], uint64_t *out /* half x 4 */);
+/* step_radix2_domain<Fr> transforms over 2^log_big + 2^log_small points (log_small < log_big), in place on a host vector:
+ * mode 0 FFT, 1 iFFT, 2 cosetFFT(g), 3 icosetFFT(g) (FQFFT/evaluation_domain/domains/step_radix2_domain.tcc:38-152).  The two
+ * radix-2 transforms inside and the O(m) loops the reference wraps around them (serial omega_i *= omega chains on the
+ * host there) run on the device; one upload and one download per call. */
+int b200_fr_step_fft(uint64_t *a /* (2^log_big + 2^log_small) x 4 */, size_t log_big, size_t log_small, int mode, const uint64_t *coset_g);
+
 /* step_radix2_domain::divide_by_Z_on_coset (FQFFT/evaluation_domain/domains/step_radix2_domain.tcc:213-241; FQFFT =
  * depends/libsnark/depends/libfqfft/libfqfft): the domain libfqfft picks for 2^k + 2^r constraints (the 128 x 128 matrix
  * product of BASELINE.json configs[3]: 2^21 + 1) divides by Z with ONE FIELD INVERSION PER POINT on the host, 95 % of the

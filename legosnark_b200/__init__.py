@@ -339,6 +339,17 @@ def mle_push_randomness(table, r):
     return out
 
 
+def fr_step_fft(a, log_big, log_small, mode=0, g=None):
+    """libfqfft's step_radix2_domain (step_radix2_domain.tcc:38-152) over 2^log_big + 2^log_small points: mode 0 FFT,
+    1 iFFT, 2 cosetFFT(g), 3 icosetFFT(g); returns the transformed copy."""
+    a = _arr(a, 4).copy()
+    if a.shape[0] != (1 << log_big) + (1 << log_small):
+        raise ValueError("step_radix2: expected a.size() == this->m")
+    g = None if g is None else _arr(g, 4)
+    _check(lib().b200_fr_step_fft(_p(a), _sz(log_big), _sz(log_small), int(mode), _p(g)), "b200_fr_step_fft")
+    return a
+
+
 def scale_inv_geometric(P, n_geo, c1, ratio, c0, tail=None):
     """P[i] *= (c1 * ratio^i - c0)^-1 for i < n_geo and P[n_geo + i] *= tail: the divisions of libfqfft's
     step_radix2_domain::divide_by_Z_on_coset (step_radix2_domain.tcc:213-241) with caller-formed constants."""

@@ -80,12 +80,19 @@ struct Device {
     cudaStream_t copy_stream = nullptr;  // H2D of the next chunk while the previous one is accumulated
     cudaEvent_t ev_ready[MAX_CHUNKS] = {};  // chunk j has landed on the device
     cudaEvent_t ev_sync = nullptr;
+    // Last use of engine-owned buffers / cached tables by a call that returned WITHOUT synchronising (the *_dev entry
+    // points run on the caller's stream): every entry point first makes its stream wait for it (engine_enter), the
+    // asynchronous ones record it when they have enqueued their work (engine_leave).  All engine streams are
+    // non-blocking, so without this a later call on another stream could read tables or scratch still being written.
+    cudaEvent_t ev_busy = nullptr;
     // inputs
     DevBuf scalars, bases_jac, bases_aff, flags, prefix;
     // sort
     DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, digits, meta, order, len_hist, len_cursor;
     // radix-partition sort (engine_sort.cu): standard-form scalars, (entry, bucket) pairs, per-partition counters
     DevBuf std_scalars, items, part;
+    // batch-affine accumulation (pair_kernels.cuh): the points of tree levels 1 and 2
+    DevBuf pa1, pa2;
     bool sort_attr_set = false;
     // accumulation / reduction
     DevBuf partial, seg_run, seg_acc, job_out, split, big, done, window_sums, bucket_sum;
@@ -113,7 +120,7 @@ struct Device {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
                          &entries, &digits, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
-                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big, &std_scalars, &items, &part};
+                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big, &std_scalars, &items, &part, &pa1, &pa2};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -128,6 +135,8 @@ struct Device {
         }
         if (ev_sync) cudaEventDestroy(ev_sync);
         ev_sync = nullptr;
+        if (ev_busy) cudaEventDestroy(ev_busy);
+        ev_busy = nullptr;
         for (auto &e : ev) {
             if (e) cudaEventDestroy(e);
             e = nullptr;
@@ -166,10 +175,14 @@ extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
 extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre, g_tune_ones, g_tune_host_horner;
 extern int g_tune_marginals;  // 1: one-window reduction by marginal sums (measured: no faster, profiles/r2c); 0 (default): bit decomposition over all segments
+extern int g_tune_ba;    // batch-affine tree levels in front of the XYZZ accumulation: 0 (off), 1 or 2
 extern int g_tune_sort;  // 1 (default): radix partition staged through shared memory; 0: round-1 global-atomics counting sort
 // set while the second MSM of a knowledge-commitment pair runs: every device still holds the
 // scalars of its shard in D.scalars from the first one, so the host-buffer paths skip that upload
 extern bool g_scalars_resident;
+
+inline void engine_enter(Device &D, cudaStream_t st) { CK(cudaStreamWaitEvent(st, D.ev_busy, 0)); }
+inline void engine_leave(Device &D, cudaStream_t st) { CK(cudaEventRecord(D.ev_busy, st)); }
 
 inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 
@@ -191,14 +204,23 @@ void for_each_shard(size_t nshards, Fn fn)
     }
     std::vector<std::thread> th;
     std::vector<std::string> errs(nshards);
-    for (size_t i = 0; i < nshards; i++)
-        th.emplace_back([&, i] {
-            try {
-                fn(i);
-            } catch (const CudaError &e) {
-                errs[i] = e.msg;
-            }
-        });
+    try {
+        for (size_t i = 0; i < nshards; i++)
+            th.emplace_back([&, i] {
+                try {
+                    fn(i);
+                } catch (const CudaError &e) {
+                    errs[i] = e.msg;
+                } catch (const std::exception &e) {
+                    errs[i] = std::string("host error in a device worker: ") + e.what();
+                } catch (...) {
+                    errs[i] = "unknown error in a device worker";
+                }
+            });
+    } catch (...) {  // thread creation failed part-way: the workers already running are joined, not abandoned
+        for (auto &t : th) t.join();
+        throw CudaError{"could not start the per-device worker threads"};
+    }
     for (auto &t : th) t.join();
     for (auto &e : errs)
         if (!e.empty()) throw CudaError{e};
@@ -227,6 +249,7 @@ const void *fr_fold_device(Device &D, const uint64_t *v, const uint64_t *r, size
 int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval);
 int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
 int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, void *stream);
+int fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *g);
 int fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t *c1, const uint64_t *ratio, const uint64_t *c0, size_t n_tail,
                            const uint64_t *tail);
 int fr_eq_table(const uint64_t *r, size_t d, uint64_t *out);

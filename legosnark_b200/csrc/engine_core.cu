@@ -30,7 +30,7 @@ std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1, g_tune_host_horner = 1;
-int g_tune_sort = 1, g_tune_marginals = 0;
+int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0;
 bool g_scalars_resident = false;
 
 static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal
@@ -113,6 +113,7 @@ int init_devices(const int *ids, int n)
             for (auto &e : D.ev) CK(cudaEventCreate(&e));
             for (auto &e : D.ev_ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&D.ev_sync, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&D.ev_busy, cudaEventDisableTiming));
         }
     } catch (const CudaError &e2) {
         g_devs.clear();
@@ -384,6 +385,11 @@ int b200_cppoly_prove_g1(uint64_t key, const uint64_t *v, const uint64_t *r, siz
     std::lock_guard<std::mutex> lk(g_mu);
     return cppoly_prove_g1(key, v, r, d, witness, eval);
 }
+int b200_fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *coset_g)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_step_fft(a, log_big, log_small, mode, coset_g);
+}
 int b200_fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t c1[4], const uint64_t ratio[4], const uint64_t c0[4], size_t n_tail,
                                 const uint64_t *tail)
 {
@@ -494,6 +500,7 @@ int b200_set_tuning_ex(const char *key, int value)
     else if (k == "use_precomputed") g_tune_pre = value;      // 0: ignore precomputed levels of a key
     else if (k == "host_horner") g_tune_host_horner = value;  // 0: the device also weights and sums the per-job results of a one-window reduction
     else if (k == "reduce_marginals") g_tune_marginals = value;  // 0: bit decomposition over all segments (round 1)
+    else if (k == "batch_affine") g_tune_ba = std::min(std::max(value, 0), 2);  // tree levels of affine pair additions before the XYZZ tail
     else if (k == "partition_sort") g_tune_sort = value;     // 0: the round-1 global-atomics counting sort
     else if (k == "ones_filter") g_tune_ones = value;         // 0: scalars equal to one go through the sort like any other
     else return fail(B200_ERR_ARG, "unknown tuning key %s", key);
@@ -538,6 +545,10 @@ int b200_imad_peak(int kind, int iters, double *ops_per_sec, double *elapsed_ms)
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 

@@ -58,6 +58,10 @@ int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -85,6 +89,10 @@ int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t 
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -126,6 +134,10 @@ int fr_eq_table(const uint64_t *r, size_t d, uint64_t *out)
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -162,6 +174,10 @@ int fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v)
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -198,6 +214,10 @@ int fr_sumcheck_round(const uint64_t *a, const uint64_t *b, const uint64_t *w, s
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -245,6 +265,10 @@ int fr_sumcheck_rounds(const uint64_t *a, const uint64_t *b, const uint64_t *r, 
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -283,6 +307,10 @@ int fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t *c1, const 
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -300,8 +328,10 @@ struct FrDomain {
 };
 static std::vector<std::map<uint32_t, std::unique_ptr<FrDomain>>> g_domains;
 
+void fr_step_release();
 void fr_release()
 {
+    fr_step_release();
     for (size_t di = 0; di < g_domains.size(); di++) {
         if (di < g_devs.size()) cudaSetDevice(g_devs[di].id);
         for (auto &kv : g_domains[di]) {
@@ -370,6 +400,7 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
         cudaStream_t st = (d_a && stream) ? (cudaStream_t)stream : D.stream;
         const uint32_t logn = (uint32_t)log_n;
         const size_t n = (size_t)1 << logn;
+        engine_enter(D, st);  // tables / D.fr_b may still be in use by an earlier asynchronous call on another stream
         FrDomain &dm = domain_for(D, 0, logn, (mode == 2 || mode == 3) ? g : nullptr, st);
         Fr *data;
         D.fr_b.ensure(n * sizeof(Fr));
@@ -417,6 +448,8 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
         if (!d_a) {
             d2h(D, a, data, n * sizeof(Fr), st);
             CK(cudaStreamSynchronize(st));
+        } else {
+            engine_leave(D, st);
         }
         g_stats = b200_stats_t{};
         g_stats.n = n;
@@ -427,6 +460,103 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
+    }
+}
+
+// ------------------------------------------------------------------------------
+// step_radix2_domain transforms (2^log_big + 2^log_small points): mode 0 FFT, 1 iFFT, 2 cosetFFT(g), 3 icosetFFT(g)
+// (step_radix2_domain.tcc:38-152).  The two radix-2 transforms inside are fr_fft on device buffers; the loops around
+// them are the k_step_* kernels.  One upload, one download.
+// ------------------------------------------------------------------------------
+static DevBuf g_st_a, g_st_c, g_st_d, g_st_e, g_st_part, g_st_gp, g_st_const;
+void fr_step_release()
+{
+    DevBuf *all[] = {&g_st_a, &g_st_c, &g_st_d, &g_st_e, &g_st_part, &g_st_gp, &g_st_const};
+    for (DevBuf *b : all) b->release();
+}
+
+int fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *g)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!a || mode < 0 || mode > 3) return fail(B200_ERR_ARG, "bad argument");
+    if (log_small >= log_big || log_big + 1 > FR_TWO_ADICITY) return fail(B200_ERR_ARG, "step_radix2: expected small_m < big_m and 2 big_m | 2^28");
+    if (mode >= 2 && !g) return fail(B200_ERR_ARG, "coset transforms need the shift g");
+    // 1/2 in Fr, Montgomery form ((r + 1) / 2 * 2^256 mod r): FieldT(2).inverse() of step_radix2_domain.tcc:127
+    static const uint32_t HALF[8] = {0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu, 0xfcfd4f45u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au};
+    try {
+        Device &D = g_devs[0];
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        const size_t big = (size_t)1 << log_big, small = (size_t)1 << log_small, m = big + small, compr = big / small;
+        const bool inverse = mode == 1 || mode == 3, coset = mode >= 2;
+        uint32_t launches = 0;
+        D.launches = 0;
+        g_st_a.ensure(m * sizeof(Fr));
+        g_st_c.ensure(big * sizeof(Fr));
+        g_st_d.ensure(big * sizeof(Fr));
+        g_st_e.ensure(small * sizeof(Fr));
+        g_st_const.ensure(8 * sizeof(Fr));
+        const uint32_t J = (uint32_t)std::max<size_t>(1, std::min<size_t>(compr, std::max<size_t>(1, ((size_t)1 << 16) / small)));
+        g_st_part.ensure((size_t)J * small * sizeof(Fr));
+        h2d(D, g_st_a.p, a, m * sizeof(Fr), st);
+        // omega^i / omega^-i, i < big: the twiddle tables of the radix-2 domain of size 2 * big (omega = its root of unity, :31)
+        FrDomain &dm2 = domain_for(D, 0, (uint32_t)log_big + 1, nullptr, st);
+        const Fr *ow = dm2.tw_fwd.as<Fr>(), *owi = dm2.tw_inv.as<Fr>();
+        const Fr *gp = nullptr;
+        Fr *cst = g_st_const.as<Fr>();
+        CK(cudaMemcpyAsync(cst + 5, HALF, sizeof(Fr), cudaMemcpyHostToDevice, st));
+        if (coset) {  // g^i (cosetFFT) or g^-i (icosetFFT), i < m
+            g_st_gp.ensure(m * sizeof(Fr));
+            CK(cudaMemcpyAsync(cst + 6, g, sizeof(Fr), cudaMemcpyHostToDevice, st));
+            LAUNCH(D, k_fr_domain_consts, 1, 32, 0, st, 1u, (const Fr *)(cst + 6), cst);  // cst[3] = g, cst[4] = g^-1
+            LAUNCH(D, k_fr_pow_table, cdiv(cdiv(m, 16), 128), 128, 0, st, (const Fr *)(cst + (inverse ? 4 : 3)), (const Fr *)nullptr, m,
+                   g_st_gp.as<Fr>());
+            gp = g_st_gp.as<Fr>();
+        }
+        Fr *A = g_st_a.as<Fr>(), *C = g_st_c.as<Fr>(), *Dd = g_st_d.as<Fr>(), *E = g_st_e.as<Fr>(), *part = g_st_part.as<Fr>();
+        launches += D.launches;
+        if (!inverse) {
+            LAUNCH(D, k_step_fwd_pre, cdiv(big, 256), 256, 0, st, (const Fr *)A, gp, ow, big, small, C, Dd);
+            LAUNCH(D, k_step_strided_partial, cdiv(small * J, 256), 256, 0, st, (const Fr *)Dd, (const Fr *)nullptr, small, compr, 0u, J, part);
+            LAUNCH(D, k_step_strided_final, cdiv(small, 256), 256, 0, st, (const Fr *)part, small, J, E);
+            launches += D.launches;
+            int rc = fr_fft(nullptr, C, log_big, 0, nullptr, st);
+            launches += D.launches;
+            if (rc == B200_OK && log_small >= 1) rc = fr_fft(nullptr, E, log_small, 0, nullptr, st);
+            if (rc != B200_OK) return rc;
+            launches += D.launches;
+            d2h(D, a, C, big * sizeof(Fr), st);
+            d2h(D, a + 4 * big, E, small * sizeof(Fr), st);
+        } else {
+            int rc = fr_fft(nullptr, A, log_big, 1, nullptr, st);
+            launches += D.launches;
+            if (rc == B200_OK && log_small >= 1) rc = fr_fft(nullptr, A + big, log_small, 1, nullptr, st);
+            if (rc != B200_OK) return rc;
+            launches += D.launches;
+            D.launches = 0;
+            LAUNCH(D, k_step_strided_partial, cdiv(small * J, 256), 256, 0, st, (const Fr *)A, ow, small, compr, 1u, J, part);
+            LAUNCH(D, k_step_strided_final, cdiv(small, 256), 256, 0, st, (const Fr *)part, small, J, E);
+            LAUNCH(D, k_step_inv_post, cdiv(big, 256), 256, 0, st, (const Fr *)A, (const Fr *)(A + big), (const Fr *)E, owi, gp, (const Fr *)(cst + 5),
+                   big, small, A);
+            launches += D.launches;
+            d2h(D, a, A, m * sizeof(Fr), st);
+        }
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = m;
+        g_stats.kernel_launches = launches;
+        g_stats.h2d_bytes = g_stats.d2h_bytes = (double)m * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 

@@ -5,13 +5,14 @@
 #include "host_arith.hpp"
 #include "host_copy.hpp"
 #include "msm_kernels.cuh"
+#include "pair_kernels.cuh"
 #include "test_ops.cuh"
 
 namespace b200 {
 namespace eng {
 
 // radix-partition bucket sort (engine_sort.cu)
-bool partition_geometry(const MsmGeom &g, size_t n, int sms, SortGeom *out);
+bool partition_geometry(const MsmGeom &g, size_t n, int sms, SortGeom *out, uint32_t align_log);
 void enqueue_partition_sort(Device &D, cudaStream_t st, const MsmGeom &g, const SortGeom &sg, const uint8_t *d_flags,
                             const Fr *d_scalars, size_t n);
 
@@ -224,7 +225,7 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.toff.ensure((size_t)g.NB * 4);
     D.tile_sums.ensure((size_t)P.ntiles * sizeof(uint2));
     D.totals.ensure(32);
-    D.entries.ensure(P.max_entries * 4);
+    D.entries.ensure((P.max_entries + (size_t)3 * g.NB + 4 * 4096 + 16) * 4);  // + alignment padding of the batch-affine path
     D.digits.ensure((size_t)g.W * ((chunk_max + 3) & ~(size_t)3) * 4);
     D.meta.ensure(P.max_tasks * sizeof(uint2));
     D.order.ensure(P.max_tasks * 4);
@@ -262,7 +263,8 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
 {
     const MsmGeom &g = P.g;
     SortGeom sg;
-    const bool part_sort = g_tune_sort && partition_geometry(g, n, D.sms, &sg);
+    const uint32_t ba = g_tune_sort ? (uint32_t)g_tune_ba : 0u;  // batch-affine tree levels (needs the aligned bucket ranges of the partition sort)
+    const bool part_sort = g_tune_sort && partition_geometry(g, n, D.sms, &sg, ba);
     if (!part_sort) {
         CK(cudaMemsetAsync(D.cnt.p, 0, (size_t)g.NB * 4, st));
         CK(cudaMemsetAsync((char *)D.totals.p + 12, 0, 4, st));  // totals[3]: scalars equal to one
@@ -294,7 +296,26 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
     LAUNCH(D, k_task_order, tblocks, 256, 2 * (g.L + 1) * 4, st, meta, totals, g, len_cursor, order);
     }
     CK(cudaEventRecord(D.ev[2], st));
-    LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
+    if (part_sort && ba) {
+        // levels of independent affine pair additions with shared inversions, then the XYZZ tail (pair_kernels.cuh)
+        const size_t slots = (size_t)g.W * n + (size_t)3 * g.NB + 4 * 4096 + 16;
+        D.prefix.ensure((slots / 2 + 1) * sizeof(F));
+        D.pa1.ensure((slots / 2 + 1) * sizeof(Affine<F>));
+        const uint32_t pblocks = (uint32_t)D.sms * 2;
+        LAUNCH(D, (k_pair_add<F, 0>), pblocks, PAIR_THREADS, 0, st, d_aff, (const uint32_t *)entries, (const Affine<F> *)nullptr,
+               (const uint32_t *)totals, D.prefix.as<F>(), D.pa1.as<Affine<F>>());
+        const Affine<F> *last = D.pa1.as<Affine<F>>();
+        if (ba >= 2) {
+            D.pa2.ensure((slots / 4 + 1) * sizeof(Affine<F>));
+            LAUNCH(D, (k_pair_add<F, 1>), pblocks, PAIR_THREADS, 0, st, d_aff, (const uint32_t *)entries, last, (const uint32_t *)totals,
+                   D.prefix.as<F>(), D.pa2.as<Affine<F>>());
+            last = D.pa2.as<Affine<F>>();
+        }
+        LAUNCH(D, (k_accumulate_pa<F>), cdiv(max_tasks, 128), 128, 0, st, last, ba, (const uint2 *)meta, (const uint32_t *)order,
+               (const uint32_t *)totals, partial);
+    } else {
+        LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
+    }
     CK(cudaEventRecord(D.ev[3], st));
     LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 8, 128, 0, st, cnt, toff, split, totals, g, partial);
     {   // hot buckets: as many passes as the largest possible bucket (all tasks in one) needs; idle ones return at once
@@ -515,6 +536,10 @@ int msm_small_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uin
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -559,6 +584,10 @@ int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t 
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -606,6 +635,10 @@ int msm_batch(const uint64_t *bases, const uint64_t *scalars, const uint64_t *of
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -647,6 +680,10 @@ int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *h
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -671,23 +708,37 @@ int key_precompute(uint64_t handle, uint32_t window_bits)
             if (S.d_pre) {
                 CK(cudaFree(S.d_pre));
                 S.d_pre = nullptr;
+                S.pre_c = S.pre_W = 0;
             }
-            CK(cudaMalloc(&S.d_pre, (size_t)W * S.count * sizeof(Affine<F>)));
-            Affine<F> *lv = reinterpret_cast<Affine<F> *>(S.d_pre);
-            CK(cudaMemcpyAsync(lv, S.d_aff, S.count * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, D.stream));
-            D.bases_jac.ensure(S.count * sizeof(Jacobian<F>));
-            for (uint32_t k = 1; k < W; k++) {
-                LAUNCH(D, (k_key_level<F>), cdiv(S.count, 128), 128, 0, D.stream, (const Affine<F> *)(lv + (size_t)(k - 1) * S.count), c,
-                       S.count, D.bases_jac.as<Jacobian<F>>());
-                run_ingest<F, false>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), lv + (size_t)k * S.count, nullptr, S.count);
+            // built into a local pointer and published (d_pre, pre_c, pre_W together) only when complete: an error
+            // half-way leaves the key as a plain key instead of one with a table but no window geometry
+            void *table = nullptr;
+            CK(cudaMalloc(&table, (size_t)W * S.count * sizeof(Affine<F>)));
+            try {
+                Affine<F> *lv = reinterpret_cast<Affine<F> *>(table);
+                CK(cudaMemcpyAsync(lv, S.d_aff, S.count * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, D.stream));
+                D.bases_jac.ensure(S.count * sizeof(Jacobian<F>));
+                for (uint32_t k = 1; k < W; k++) {
+                    LAUNCH(D, (k_key_level<F>), cdiv(S.count, 128), 128, 0, D.stream, (const Affine<F> *)(lv + (size_t)(k - 1) * S.count), c,
+                           S.count, D.bases_jac.as<Jacobian<F>>());
+                    run_ingest<F, false>(D, D.stream, D.bases_jac.as<Jacobian<F>>(), lv + (size_t)k * S.count, nullptr, S.count);
+                }
+                CK(cudaStreamSynchronize(D.stream));
+            } catch (...) {
+                cudaFree(table);
+                throw;
             }
-            CK(cudaStreamSynchronize(D.stream));
+            S.d_pre = table;
             S.pre_c = c;
             S.pre_W = W;
         });
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -702,7 +753,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
     auto it = g_pinned.find(handle);
     if (it == g_pinned.end() || it->second->group != HostOf<F>::group) return fail(B200_ERR_ARG, "unknown bases handle");
     PinnedBases &pb = *it->second;
-    if (!out || offset + n > pb.n || (n && !scalars && !d_scalars)) return fail(B200_ERR_ARG, "bad range or null argument");
+    if (!out || offset > pb.n || n > pb.n - offset || (n && !scalars && !d_scalars)) return fail(B200_ERR_ARG, "bad range or null argument");
     if (d_scalars && pb.shards.size() != 1) return fail(B200_ERR_ARG, "device-resident scalars need a single-device key");
     if (n == 0) {
         write_point<HF>(out, J::inf());
@@ -719,6 +770,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
             const size_t lo = std::max(offset, S.begin), hi = std::min(offset + n, S.begin + S.count);
             if (lo < hi) pieces.push_back({si, lo, hi - lo});
         }
+        if (pieces.empty()) return fail(B200_ERR_ARG, "range does not intersect the key");
         std::vector<MsmGeom> geoms(pieces.size());
         for (auto &d : g_devs) d.launches = 0;
         for_each_shard(pieces.size(), [&](size_t pi) {
@@ -727,6 +779,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
             Device &D = g_devs[S.dev];
             CK(cudaSetDevice(D.id));
             cudaStream_t st = (d_scalars && stream) ? (cudaStream_t)stream : D.stream;
+            engine_enter(D, st);
             const Fr *ds;
             if (d_scalars) {
                 ds = reinterpret_cast<const Fr *>(d_scalars);
@@ -789,6 +842,10 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -858,6 +915,10 @@ int table_create(const uint64_t *base, size_t expected, uint64_t *handle)
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -882,6 +943,7 @@ int batch_exp_table(uint64_t handle, const uint64_t *scalars, const void *d_scal
             if (m == 0) return;
             CK(cudaSetDevice(D.id));
             cudaStream_t st = (dev_io && stream) ? (cudaStream_t)stream : D.stream;
+            engine_enter(D, st);
             const Fr *ds;
             if (dev_io) {
                 ds = reinterpret_cast<const Fr *>(d_scalars);
@@ -901,6 +963,7 @@ int batch_exp_table(uint64_t handle, const uint64_t *scalars, const void *d_scal
                    D.out_jac.as<Jacobian<F>>());
             if (dev_io) {
                 run_ingest<F, false>(D, st, D.out_jac.as<Jacobian<F>>(), d_out_affine, nullptr, m);
+                engine_leave(D, st);  // returns without synchronising: D.out_jac / D.prefix stay busy on `st`
             } else {
                 D.out_norm.ensure(m * sizeof(Jacobian<F>));
                 run_ingest<F, true>(D, st, D.out_jac.as<Jacobian<F>>(), D.out_norm.p, nullptr, m);
@@ -918,6 +981,10 @@ int batch_exp_table(uint64_t handle, const uint64_t *scalars, const void *d_scal
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -960,6 +1027,10 @@ int batch_to_affine(uint64_t *pts, size_t n)
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -1007,6 +1078,10 @@ int run_elementwise(const uint64_t *a, const uint64_t *b, size_t n, uint64_t *ou
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 

@@ -7,7 +7,7 @@ namespace b200 {
 namespace eng {
 
 // partition geometry for NB buckets, or false when the bucket set is outside what the shared-memory passes cover
-bool partition_geometry(const MsmGeom &g, size_t n, int sms, SortGeom *out)
+bool partition_geometry(const MsmGeom &g, size_t n, int sms, SortGeom *out, uint32_t align_log)
 {
     uint32_t lg = 0;
     while (((uint64_t)1 << lg) < g.NB) lg++;
@@ -16,6 +16,7 @@ bool partition_geometry(const MsmGeom &g, size_t n, int sms, SortGeom *out)
     const uint64_t NP = ((uint64_t)g.NB + ((1u << low) - 1)) >> low;
     if (NP > PART_MAX_NP || g.W > PART_STAGE_ITEMS / 32 || g.L + 1 > 2048) return false;
     SortGeom sg;
+    sg.align_log = align_log;
     sg.low_bits = low;
     sg.NP = (uint32_t)NP;
     sg.tile = std::min<uint32_t>(SCAT_THREADS, PART_STAGE_ITEMS / g.W);
@@ -44,7 +45,8 @@ void enqueue_partition_sort(Device &D, cudaStream_t st, const MsmGeom &g, const 
 {
     set_sort_attributes(D);
     D.std_scalars.ensure(n * sizeof(Fr));
-    D.items.ensure((size_t)g.W * n * sizeof(uint2));
+    const uint32_t amask = (1u << sg.align_log) - 1u, pad = amask << sg.low_bits;  // at most 2^align_log - 1 padding slots per bucket
+    D.items.ensure(((size_t)g.W * n + (size_t)sg.NP * (pad + amask + 1)) * sizeof(uint2));
     D.part.ensure((size_t)PART_MAX_NP * 5 * 4);
     uint32_t *pcount = D.part.as<uint32_t>(), *pstart = pcount + PART_MAX_NP, *pcursor = pstart + PART_MAX_NP;
     uint32_t *ptasks = pcursor + PART_MAX_NP, *ptstart = ptasks + PART_MAX_NP;
@@ -56,14 +58,14 @@ void enqueue_partition_sort(Device &D, cudaStream_t st, const MsmGeom &g, const 
     Fr *stdsc = D.std_scalars.as<Fr>();
     LAUNCH(D, k_part_hist, cdiv(n, sg.hist_per_block), PART_THREADS, (size_t)sg.NP * 4, st, d_scalars, d_flags, n, g, sg, stdsc, pcount,
            g.ones ? D.ones_idx.as<uint32_t>() : (uint32_t *)nullptr, totals + 3);
-    LAUNCH(D, k_part_scan, 1, 1024, 0, st, (const uint32_t *)pcount, sg.NP, pstart, pcursor, totals + 0, (uint32_t *)nullptr, (uint32_t *)nullptr,
-           (const uint32_t *)nullptr, (uint32_t *)nullptr, 0u);
+    LAUNCH(D, k_part_scan, 1, 1024, 0, st, (const uint32_t *)pcount, sg.NP, pstart, pcursor, totals + 5, (uint32_t *)nullptr, (uint32_t *)nullptr,
+           (const uint32_t *)nullptr, (uint32_t *)nullptr, 0u, pad, amask, totals + 0);  // totals[0]: entries; totals[5]: slots incl. padding
     LAUNCH(D, k_part_scatter, cdiv(n, sg.tile), SCAT_THREADS, part_scatter_smem(sg), st, (const Fr *)stdsc, n, g, sg, pcursor,
            D.items.as<uint2>());
     LAUNCH(D, k_part_sort, sg.NP, FINE_THREADS, part_sort_smem(sg, g.L), st, (const uint2 *)D.items.as<uint2>(), (const uint32_t *)pstart,
            (const uint32_t *)pcount, g, sg, D.cnt.as<uint32_t>(), D.off.as<uint32_t>(), D.entries.as<uint32_t>(), ptasks, len_hist);
     LAUNCH(D, k_part_scan, 1, 1024, 0, st, (const uint32_t *)ptasks, sg.NP, ptstart, (uint32_t *)nullptr, totals + 1, totals + 2, totals + 4,
-           (const uint32_t *)len_hist, len_cursor, g.L);
+           (const uint32_t *)len_hist, len_cursor, g.L, 0u, 0u, (uint32_t *)nullptr);
     LAUNCH(D, k_task_emit, sg.NP, FINE_THREADS, task_emit_smem(sg, g.L), st, (const uint32_t *)D.cnt.as<uint32_t>(),
            (const uint32_t *)D.off.as<uint32_t>(), (const uint32_t *)ptstart, g, sg, D.toff.as<uint32_t>(), D.meta.as<uint2>(),
            D.order.as<uint32_t>(), totals, D.split.as<uint32_t>(), D.big.as<uint32_t>(), len_cursor);

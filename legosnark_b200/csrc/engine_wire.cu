@@ -43,6 +43,10 @@ static int compress_points(const uint64_t *pts, size_t n, int fl, uint64_t *x_ou
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 
@@ -83,6 +87,10 @@ static int decompress_points(const uint64_t *x, const uint8_t *flags, size_t n, 
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
     }
 }
 

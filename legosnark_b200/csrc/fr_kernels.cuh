@@ -291,6 +291,82 @@ static __global__ void __launch_bounds__(256) k_fr_scale(Fr *__restrict__ P, siz
     if (i < n) P[i] = Fr::mul(P[i], *s);
 }
 
+// ------------------------------------------------------------------------------
+// step_radix2_domain (FQFFT/evaluation_domain/domains/step_radix2_domain.tcc): domains of 2^k + 2^r points, the one
+// libfqfft picks for the 128 x 128 matrix product of BASELINE.json configs[3] (2^21 + 1).  The two radix-2 transforms
+// inside run through k_fr_fft_pass; these kernels are the O(m) loops the reference wraps around them (:38-71, :73-139),
+// which are serial host code there (omega_i *= omega chains).  ow[] = omega^i, i < big (the twiddle table of the
+// 2 * big domain); gp[] = g^i, i < big + small, for the coset variants (_multiply_by_coset, aux.tcc:172-180).
+// ------------------------------------------------------------------------------
+// FFT, first loop (:43-50): c[i] = a[i] + a[i+big], d[i] = omega^i (a[i] - a[i+big]) for i < small; c[i] = a[i], d[i] = omega^i a[i] above
+static __global__ void __launch_bounds__(256) k_step_fwd_pre(const Fr *__restrict__ a, const Fr *__restrict__ gp, const Fr *__restrict__ ow,
+                                                             size_t big, size_t small, Fr *__restrict__ c, Fr *__restrict__ d)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= big) return;
+    Fr lo = a[i];
+    if (gp) lo = Fr::mul(lo, gp[i]);
+    if (i < small) {
+        Fr hi = a[i + big];
+        if (gp) hi = Fr::mul(hi, gp[i + big]);
+        c[i] = Fr::add(lo, hi);
+        d[i] = Fr::mul(ow[i], Fr::sub(lo, hi));
+    } else {
+        c[i] = lo;
+        d[i] = Fr::mul(ow[i], lo);
+    }
+}
+
+// part[jc * small + i] = sum over j = j0 + jc, j0 + jc + J, ... < compr of (scale ? scale[i + j small] : 1) * d[i + j small]
+// (the e[i] sums of FFT :52-60 with j0 = 0; the U1[i] -= sum tmp[i + j small] of iFFT :113-120 with j0 = 1 and scale = omega^i)
+static __global__ void __launch_bounds__(256) k_step_strided_partial(const Fr *__restrict__ d, const Fr *__restrict__ scale, size_t small,
+                                                                     size_t compr, uint32_t j0, uint32_t J, Fr *__restrict__ part)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= small * J) return;
+    const size_t i = t % small, jc = t / small;
+    Fr acc = Fr::zero();
+    for (size_t j = j0 + jc; j < compr; j += J) {
+        Fr v = d[i + j * small];
+        if (scale) v = Fr::mul(v, scale[i + j * small]);
+        acc = Fr::add(acc, v);
+    }
+    part[jc * small + i] = acc;
+}
+// out[i] = sum_jc part[jc small + i]
+static __global__ void __launch_bounds__(256) k_step_strided_final(const Fr *__restrict__ part, size_t small, uint32_t J, Fr *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= small) return;
+    Fr acc = part[i];
+    for (uint32_t jc = 1; jc < J; jc++) acc = Fr::add(acc, part[(size_t)jc * small + i]);
+    out[i] = acc;
+}
+
+// iFFT, last loops (:106-138) given U0 = iFFT_big(a[0..big)), U1 = iFFT_small(a[big..)), S[i] = sum_{j >= 1} omega^(i + j small) U0[i + j small]:
+//   U1'[i] = (U1[i] - S[i]) omega^-i;  a[i] = (U0[i] + U1'[i]) / 2, a[big + i] = (U0[i] - U1'[i]) / 2 for i < small;  a[i] = U0[i] above;
+// then the optional coset scaling a[i] *= g^-i (icosetFFT :148-152).  owi[] = omega^-i; half = 1/2.
+static __global__ void __launch_bounds__(256) k_step_inv_post(const Fr *__restrict__ U0, const Fr *__restrict__ U1, const Fr *__restrict__ S,
+                                                              const Fr *__restrict__ owi, const Fr *__restrict__ gip, const Fr *__restrict__ half,
+                                                              size_t big, size_t small, Fr *__restrict__ a)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= big) return;
+    const Fr u0 = U0[i];
+    if (i < small) {
+        const Fr u1 = Fr::mul(Fr::sub(U1[i], S[i]), owi[i]);
+        Fr lo = Fr::mul(Fr::add(u0, u1), *half), hi = Fr::mul(Fr::sub(u0, u1), *half);
+        if (gip) {
+            lo = Fr::mul(lo, gip[i]);
+            hi = Fr::mul(hi, gip[i + big]);
+        }
+        a[i] = lo;
+        a[i + big] = hi;
+    } else {
+        a[i] = gip ? Fr::mul(u0, gip[i]) : u0;
+    }
+}
+
 constexpr int FFT_THREADS = 256;
 constexpr int FFT_TILE_LOG = 10;  // a block holds 2^10 elements = 32 KB of shared memory
 

@@ -61,7 +61,12 @@ struct SortGeom {
     uint32_t NP;              // partitions = ceil(NB / 2^low_bits)
     uint32_t tile;            // scalars per block of k_part_scatter (W * tile <= PART_STAGE_ITEMS)
     uint32_t hist_per_block;  // scalars per block of k_part_hist (multiple of 256)
+    // batch-affine accumulation (pair_kernels.cuh): every bucket's range of `entries` starts on a multiple of 2^align_log
+    // slots and is padded with ENTRY_PAD up to one, so that slots (2q, 2q+1), (4r .. 4r+3) never straddle buckets.
+    // 0: dense ranges as in round 1.
+    uint32_t align_log;
 };
+constexpr uint32_t ENTRY_PAD = 0xffffffffu;  // no point index reaches 2^31 - 1 (W n < 2^31 is checked for keys; sign bit set + all ones)
 __host__ __device__ __forceinline__ uint32_t result_points(const MsmGeom &g) { return g.red_jobs ? g.red_jobs : g.Wb; }
 __host__ __device__ __forceinline__ uint32_t bucket_base(const MsmGeom &g, uint32_t k) { return g.pre_stride ? 0u : k * g.B; }
 

@@ -132,12 +132,24 @@ static __global__ void __launch_bounds__(PART_THREADS) k_part_hist(const Fr *__r
 static __global__ void __launch_bounds__(1024) k_part_scan(const uint32_t *__restrict__ count, uint32_t NP, uint32_t *__restrict__ start,
                                                             uint32_t *__restrict__ cursor, uint32_t *__restrict__ total_out,
                                                             uint32_t *__restrict__ zero_a, uint32_t *__restrict__ zero_b,
-                                                            const uint32_t *__restrict__ len_hist, uint32_t *__restrict__ len_cursor, uint32_t L)
+                                                            const uint32_t *__restrict__ len_hist, uint32_t *__restrict__ len_cursor, uint32_t L,
+                                                            uint32_t pad, uint32_t align_mask, uint32_t *__restrict__ raw_total_out)
 {
     __shared__ uint32_t sh[PART_MAX_NP];
     __shared__ uint32_t tmp[33];
-    for (uint32_t p = threadIdx.x; p < NP; p += 1024) sh[p] = count[p];
+    __shared__ uint32_t raw;
+    if (threadIdx.x == 0) raw = 0;
     __syncthreads();
+    // pad / align_mask != 0: room for the per-bucket alignment padding of the partition (SortGeom::align_log)
+    uint32_t mine = 0;
+    for (uint32_t p = threadIdx.x; p < NP; p += 1024) {
+        const uint32_t c = count[p];
+        mine += c;
+        sh[p] = (c + pad + align_mask) & ~align_mask;
+    }
+    if (mine) atomicAdd(&raw, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && raw_total_out) *raw_total_out = raw;
     const uint32_t total = block_excl_scan(sh, NP, tmp);
     for (uint32_t p = threadIdx.x; p < NP; p += 1024) {
         start[p] = sh[p];
@@ -240,6 +252,7 @@ static __global__ void __launch_bounds__(FINE_THREADS) k_part_sort(const uint2 *
     const uint32_t p = blockIdx.x, b0 = p << sg.low_bits;
     const uint32_t nb = min(PB, g.NB - b0);
     const uint32_t ps = pstart[p], pc = pcount[p];
+    const uint32_t amask = (1u << sg.align_log) - 1u;
     for (uint32_t b = threadIdx.x; b < PB; b += FINE_THREADS) cnt_sh[b] = 0;
     for (uint32_t k = threadIdx.x; k <= L; k += FINE_THREADS) lh[k] = 0;
     if (threadIdx.x == 0) sh_tasks = 0;
@@ -258,7 +271,7 @@ static __global__ void __launch_bounds__(FINE_THREADS) k_part_sort(const uint2 *
     uint32_t t = 0;
     for (uint32_t b = threadIdx.x; b < PB; b += FINE_THREADS) {
         const uint32_t c = cnt_sh[b];
-        cur_sh[b] = c;
+        cur_sh[b] = (c + amask) & ~amask;  // slots of the bucket: its entries, padded to the alignment
         if (b < nb) {
             cnt[b0 + b] = c;
             t += tasks_of(c, L);
@@ -273,13 +286,23 @@ static __global__ void __launch_bounds__(FINE_THREADS) k_part_sort(const uint2 *
     for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
     if ((threadIdx.x & 31u) == 0 && t) atomicAdd(&sh_tasks, t);
     __syncthreads();
-    block_excl_scan(cur_sh, PB, tmp);
+    const uint32_t slots = block_excl_scan(cur_sh, PB, tmp);  // == pc without alignment
     for (uint32_t b = threadIdx.x; b < nb; b += FINE_THREADS) off[b0 + b] = ps + cur_sh[b];
     for (uint32_t k = threadIdx.x; k <= L; k += FINE_THREADS)
         if (lh[k]) atomicAdd(&len_hist[k], lh[k]);
     if (threadIdx.x == 0) ptasks[p] = sh_tasks;
     __syncthreads();
-    const bool staged = pc <= FINE_STAGE;
+    const bool staged = slots <= FINE_STAGE;
+    if (amask) {  // padding slots read as ENTRY_PAD; the real entries overwrite their slots after the barrier
+        for (uint32_t j = threadIdx.x; j < slots; j += FINE_THREADS) {
+            if (staged) stage[j] = ENTRY_PAD;
+            else entries[ps + j] = ENTRY_PAD;
+        }
+        // the unused end of the partition's region (it was sized for the worst-case padding, k_part_scan)
+        const uint32_t alloc = (pc + (amask << sg.low_bits) + amask) & ~amask;
+        for (uint32_t j = slots + threadIdx.x; j < alloc; j += FINE_THREADS) entries[ps + j] = ENTRY_PAD;
+        __syncthreads();
+    }
     for (uint32_t basej = 0; basej < pc; basej += FINE_UNROLL * FINE_THREADS) {
         uint2 it[FINE_UNROLL];
 #pragma unroll
@@ -299,7 +322,7 @@ static __global__ void __launch_bounds__(FINE_THREADS) k_part_sort(const uint2 *
     }
     if (staged) {
         __syncthreads();
-        for (uint32_t j = threadIdx.x; j < pc; j += FINE_THREADS) entries[ps + j] = stage[j];
+        for (uint32_t j = threadIdx.x; j < slots; j += FINE_THREADS) entries[ps + j] = stage[j];
     }
 }
 

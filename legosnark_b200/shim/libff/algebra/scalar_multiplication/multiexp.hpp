@@ -36,7 +36,14 @@
 namespace libff {
 namespace b200_detail {
 
-template <typename T, typename FieldT, multi_exp_method Method, bool OnGpu = b200shim::group_traits<T>::supported>
+// the engine serves the four BN254 groups with their own scalar field; any other instantiation (another group, or a
+// supported group with a foreign FieldT) keeps the reference's template
+template <typename T, typename FieldT, bool Supported = b200shim::group_traits<T>::supported>
+struct on_gpu : std::false_type {};
+template <typename T, typename FieldT>
+struct on_gpu<T, FieldT, true> : std::is_same<FieldT, typename T::scalar_field> {};
+
+template <typename T, typename FieldT, multi_exp_method Method, bool OnGpu = on_gpu<T, FieldT>::value>
 struct msm_dispatch {
     typedef typename std::vector<T>::const_iterator TI;
     typedef typename std::vector<FieldT>::const_iterator SI;
@@ -69,9 +76,16 @@ struct msm_dispatch<T, FieldT, Method, true> {
 // A lazy window table is one row {0, g}: the engine builds its own affine table on the
 // device, and no caller indexes the reference's.
 template <typename T>
-inline bool is_lazy_table(const size_t scalar_size, const size_t window, const window_table<T> &t)
+inline bool is_lazy_table(const size_t, const size_t, const window_table<T> &t)
 {
-    return t.size() == 1 && t[0].size() == 2 && scalar_size > window;
+    return t.size() == 1 && t[0].size() == 2;  // what table_dispatch<T, true>::make returns, whatever (scalar_size, window) say
+}
+// row 0 of any window table is {0, g, 2g, ...} (multiexp.tcc:563-578): t[0][1] is the base
+template <typename T>
+inline const T &table_base(const window_table<T> &t)
+{
+    if (t.empty() || t[0].size() < 2) throw std::runtime_error("window_table has no base entry (expected row 0 = {0, g, ...})");
+    return t[0][1];
 }
 
 template <typename T, bool OnGpu = b200shim::group_traits<T>::supported>
@@ -106,15 +120,14 @@ struct table_dispatch<T, true> {
     template <typename FieldT>
     static T one_exp(const size_t scalar_size, const size_t window, const window_table<T> &t, const FieldT &pow)
     {
-        if (is_lazy_table(scalar_size, window, t)) return pow * t[0][1];
+        if (is_lazy_table(scalar_size, window, t)) return pow * table_base(t);
         return libff_cpu_windowed_exp<T, FieldT>(scalar_size, window, t, pow);
     }
     template <typename FieldT>
     static std::vector<T> many(const size_t, const size_t, const window_table<T> &t, const FieldT *coeff,
                                const std::vector<FieldT> &v)
     {
-        // row 0 of any window table is {0, g, 2g, ...} (multiexp.tcc:563-578): t[0][1] is the base
-        return b200shim::fixed_base_exp<T, FieldT>(t[0][1], v, coeff);
+        return b200shim::fixed_base_exp<T, FieldT>(table_base(t), v, coeff);
     }
     static void special(std::vector<T> &vec) { b200shim::to_special<T>(vec); }
 };

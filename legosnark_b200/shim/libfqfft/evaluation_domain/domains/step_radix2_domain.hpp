@@ -4,7 +4,10 @@
 // for i < big_m, serial, ~3 us each through mpn_gcdext): 6 s of the 6.9 s Groth16 prover of the 128 x 128 matrix product
 // (2^21 + 1 constraints -> this domain), BASELINE.json configs[3].  Here the host forms the four constants exactly as
 // the reference does and the device inverts the denominators in batches (b200_fr_scale_inv_geometric).
-// The transforms of this domain already reach the engine through _basic_radix2_FFT (basic_radix2_domain_aux.hpp).
+// FFT / iFFT / cosetFFT / icosetFFT are specialised as well: the reference runs the two radix-2 transforms inside them
+// through _basic_radix2_FFT (which the engine already serves) but wraps them in serial O(m) host loops
+// (omega_i *= omega chains, :43-50, :95-101, :118-124; _multiply_by_coset, aux.tcc:172-180) that cost more than the
+// transforms; b200_fr_step_fft runs the whole member on the device with one upload and one download.
 #ifndef B200_SHIM_STEP_RADIX2_DOMAIN_HPP_
 #define B200_SHIM_STEP_RADIX2_DOMAIN_HPP_
 
@@ -15,6 +18,42 @@
 #include <libfqfft/evaluation_domain/domains/basic_radix2_domain_aux.hpp>
 
 namespace libfqfft {
+
+namespace b200_detail {
+inline void step_fft(std::vector<libff::Fr<libff::default_ec_pp>> &a, size_t m, size_t big_m, size_t small_m, int mode,
+                     const libff::Fr<libff::default_ec_pp> *g)
+{
+    static_assert(sizeof(libff::Fr<libff::default_ec_pp>) == 32, "unexpected scalar layout");
+    if (a.size() != m) throw DomainSizeException("step_radix2: expected a.size() == this->m");
+    ensure_engine();
+    if (b200_fr_step_fft(reinterpret_cast<uint64_t *>(a.data()), libff::log2(big_m), libff::log2(small_m), mode,
+                         reinterpret_cast<const uint64_t *>(g)) != B200_OK)
+        throw std::runtime_error(std::string("b200_fr_step_fft failed: ") + b200_last_error());
+}
+}  // namespace b200_detail
+
+template <>
+inline void step_radix2_domain<libff::Fr<libff::default_ec_pp>>::FFT(std::vector<libff::Fr<libff::default_ec_pp>> &a)
+{
+    b200_detail::step_fft(a, this->m, big_m, small_m, 0, nullptr);
+}
+template <>
+inline void step_radix2_domain<libff::Fr<libff::default_ec_pp>>::iFFT(std::vector<libff::Fr<libff::default_ec_pp>> &a)
+{
+    b200_detail::step_fft(a, this->m, big_m, small_m, 1, nullptr);
+}
+template <>
+inline void step_radix2_domain<libff::Fr<libff::default_ec_pp>>::cosetFFT(std::vector<libff::Fr<libff::default_ec_pp>> &a,
+                                                                          const libff::Fr<libff::default_ec_pp> &g)
+{
+    b200_detail::step_fft(a, this->m, big_m, small_m, 2, &g);
+}
+template <>
+inline void step_radix2_domain<libff::Fr<libff::default_ec_pp>>::icosetFFT(std::vector<libff::Fr<libff::default_ec_pp>> &a,
+                                                                           const libff::Fr<libff::default_ec_pp> &g)
+{
+    b200_detail::step_fft(a, this->m, big_m, small_m, 3, &g);
+}
 
 template <>
 inline void step_radix2_domain<libff::Fr<libff::default_ec_pp>>::divide_by_Z_on_coset(std::vector<libff::Fr<libff::default_ec_pp>> &P)

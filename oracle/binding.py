@@ -259,6 +259,21 @@ class Checker:
         self._lscall("fr_mle_bind", _ptr(table), ctypes.c_size_t(half), _ptr(r), _ptr(out))
         return out
 
+    def fr_step_fft(self, a, log_big, log_small, mode=0, g=None):
+        """libfqfft step_radix2_domain over 2^log_big + 2^log_small points; modes as fr_fft (0..3)"""
+        a = _c(a, 4).copy()
+        assert a.shape[0] == (1 << log_big) + (1 << log_small)
+        g = None if g is None else _c(g, 4)
+        self._lscall("fr_step_fft", _ptr(a), ctypes.c_size_t(log_big), ctypes.c_size_t(log_small), int(mode), _ptr(g))
+        return a
+
+    def fr_step_divide_z(self, a, log_big, log_small):
+        """reference only: step_radix2_domain::divide_by_Z_on_coset"""
+        assert self.kind == "ref"
+        a = _c(a, 4).copy()
+        self._lscall("fr_step_divide_z", _ptr(a), ctypes.c_size_t(log_big), ctypes.c_size_t(log_small))
+        return a
+
     # -- sum-check tables (LS/prototools/mle.h, LS/gadgets/sumcheck.h) --------------------
     def fr_eq_table(self, r):
         r = _c(r, 4)

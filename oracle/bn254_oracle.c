@@ -778,6 +778,81 @@ int orc_fr_fft(uint64_t *a_, size_t log_n, int mode, const uint64_t *g_)
 }
 
 
+/* step_radix2_domain<Fr>::FFT / iFFT / cosetFFT / icosetFFT: FQFFT/evaluation_domain/domains/step_radix2_domain.tcc:38-152
+ * (FQFFT = depends/libsnark/depends/libfqfft/libfqfft), domains of big + small = 2^log_big + 2^log_small points.
+ * mode 0 FFT, 1 iFFT, 2 cosetFFT(g), 3 icosetFFT(g); in place.  The radix-2 transforms inside are orc_fr_fft modes 0 / 4
+ * (_basic_radix2_FFT with omega^2 resp. the small root, and their inverses). */
+int orc_fr_step_fft(uint64_t *a_, size_t log_big, size_t log_small, int mode, const uint64_t *g_)
+{
+    fp_t *a = (fp_t *)a_;
+    const size_t big = (size_t)1 << log_big, small = (size_t)1 << log_small, m = big + small, compr = big / small;
+    if (log_small >= log_big || log_big + 1 > 28 || mode < 0 || mode > 3 || (mode >= 2 && !g_)) return 1;
+    fp_t omega, g;
+    fr_root_of_unity(&omega, log_big + 1); /* :31: get_root_of_unity(1 << log2(m)), log2 = ceil */
+    if (g_) memcpy(&g, g_, sizeof g);
+    if (mode == 0 || mode == 2) {
+        if (mode == 2) fr_multiply_by_coset(a, m, &g); /* :142-146 */
+        fp_t *c = (fp_t *)malloc(big * sizeof(fp_t)), *d = (fp_t *)malloc(big * sizeof(fp_t)), *e = (fp_t *)calloc(small, sizeof(fp_t));
+        if (!c || !d || !e) return 1;
+        fp_t omega_i = FR.one, t;
+        for (size_t i = 0; i < big; ++i) { /* :43-50 */
+            if (i < small) {
+                fr_add(&c[i], &a[i], &a[i + big]);
+                fr_sub(&t, &a[i], &a[i + big]);
+            } else {
+                c[i] = a[i];
+                t = a[i];
+            }
+            fr_mul(&d[i], &omega_i, &t);
+            fr_mul(&omega_i, &omega_i, &omega);
+        }
+        for (size_t i = 0; i < small; ++i) /* :52-60 */
+            for (size_t j = 0; j < compr; ++j) fr_add(&e[i], &e[i], &d[i + j * small]);
+        orc_fr_fft((uint64_t *)c, log_big, 0, NULL);                  /* _basic_radix2_FFT(c, omega.squared()) */
+        if (log_small >= 1) orc_fr_fft((uint64_t *)e, log_small, 0, NULL); /* size 1: the identity */
+        memcpy(a, c, big * sizeof(fp_t));
+        memcpy(a + big, e, small * sizeof(fp_t));
+        free(c); free(d); free(e);
+        return 0;
+    }
+    /* iFFT :73-139 */
+    fp_t *U0 = (fp_t *)malloc(big * sizeof(fp_t)), *U1 = (fp_t *)malloc(small * sizeof(fp_t)), *tmp = (fp_t *)malloc(big * sizeof(fp_t));
+    if (!U0 || !U1 || !tmp) return 1;
+    memcpy(U0, a, big * sizeof(fp_t));
+    memcpy(U1, a + big, small * sizeof(fp_t));
+    orc_fr_fft((uint64_t *)U0, log_big, 1, NULL); /* unscaled inverse, then * big^-1 (:80-87) = the scaled iFFT */
+    if (log_small >= 1) orc_fr_fft((uint64_t *)U1, log_small, 1, NULL);
+    fp_t omega_i = FR.one;
+    for (size_t i = 0; i < big; ++i) { /* :95-101 */
+        fr_mul(&tmp[i], &U0[i], &omega_i);
+        fr_mul(&omega_i, &omega_i, &omega);
+    }
+    for (size_t i = small; i < big; ++i) a[i] = U0[i]; /* :104-107 */
+    for (size_t i = 0; i < small; ++i)                   /* :110-116 */
+        for (size_t j = 1; j < compr; ++j) fr_sub(&U1[i], &U1[i], &tmp[i + j * small]);
+    fp_t omega_inv, omega_inv_i = FR.one, two, over_two, t;
+    fp_inv(&omega_inv, &omega, &FR);
+    for (size_t i = 0; i < small; ++i) { /* :118-124 */
+        fr_mul(&U1[i], &U1[i], &omega_inv_i);
+        fr_mul(&omega_inv_i, &omega_inv_i, &omega_inv);
+    }
+    fr_add(&two, &FR.one, &FR.one);
+    fp_inv(&over_two, &two, &FR);
+    for (size_t i = 0; i < small; ++i) { /* :127-138 */
+        fr_add(&t, &U0[i], &U1[i]);
+        fr_mul(&a[i], &t, &over_two);
+        fr_sub(&t, &U0[i], &U1[i]);
+        fr_mul(&a[big + i], &t, &over_two);
+    }
+    free(U0); free(U1); free(tmp);
+    if (mode == 3) { /* :148-152 */
+        fp_t ginv;
+        fp_inv(&ginv, &g, &FR);
+        fr_multiply_by_coset(a, m, &ginv);
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* wire format: point compression               */
 /* operator<< / operator>> of alt_bn128_G1 (alt_bn128_g1.cpp:404-459),  */

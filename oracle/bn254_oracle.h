@@ -74,6 +74,7 @@ int orc_sha512_rng_fr(uint64_t idx0, size_t n, uint64_t *out);
 int orc_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval);
 int orc_fr_eval_mle(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *out);
 int orc_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
+int orc_fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *g);
 int orc_fr_eq_table(const uint64_t *r, size_t d, uint64_t *out);
 int orc_fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v);
 int orc_fr_sumcheck_round(const uint64_t *a, const uint64_t *b, const uint64_t *w, size_t half, uint64_t *out);

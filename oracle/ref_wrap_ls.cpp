@@ -10,6 +10,8 @@
 //   ref_sumcheck_h_polys  the round loop of CPSumcheck::prove (src/gadgets/sumcheck.cc:56-70): make_new_h_poly
 //                         (src/gadgets/sumcheck.h:85-106) + pushRandomness, with DPBeta or DPBetaDummy
 //   ref_fr_beta_suffix    DPBeta's suffix table after precomputeAll (src/prototools/mle.h:130-150)
+//   ref_fr_step_fft       libfqfft step_radix2_domain   (libfqfft/evaluation_domain/domains/step_radix2_domain.tcc:38-152)
+//   ref_fr_step_divide_z  step_radix2_domain::divide_by_Z_on_coset (:213-241)
 //   ref_fr_fft            libfqfft basic_radix2_domain  (libfqfft/evaluation_domain/domains/basic_radix2_domain.tcc)
 // LegoSNARK compiles with CURVE=BN128 only: LFr = bn128 Fr, same Montgomery limbs as
 // alt_bn128's.
@@ -22,6 +24,7 @@ using namespace std;
 #include "mle.h"
 #include "sumcheck.h"
 #include <libfqfft/evaluation_domain/domains/basic_radix2_domain.hpp>
+#include <libfqfft/evaluation_domain/domains/step_radix2_domain.hpp>
 
 namespace {
 void init_once()
@@ -68,6 +71,33 @@ int ref_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint6
     DPMle mle(d, 2 * half, load_fr(table, 2 * half));
     mle.pushRandomness(load_fr(r, 1)[0], 0);
     for (size_t p = 0; p < half; p++) store_fr(out + 4 * p, mle.getVTable(0, p));
+    return 0;
+}
+
+int ref_fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *g)
+{
+    init_once();
+    const size_t m = ((size_t)1 << log_big) + ((size_t)1 << log_small);
+    libfqfft::step_radix2_domain<LFr> dom(m);
+    vector<LFr> v = load_fr(a, m);
+    const LFr gg = g ? load_fr(g, 1)[0] : LFr::one();
+    if (mode == 0) dom.FFT(v);
+    else if (mode == 1) dom.iFFT(v);
+    else if (mode == 2) dom.cosetFFT(v, gg);
+    else if (mode == 3) dom.icosetFFT(v, gg);
+    else return 1;
+    for (size_t i = 0; i < m; i++) store_fr(a + 4 * i, v[i]);
+    return 0;
+}
+
+int ref_fr_step_divide_z(uint64_t *a, size_t log_big, size_t log_small)
+{
+    init_once();
+    const size_t m = ((size_t)1 << log_big) + ((size_t)1 << log_small);
+    libfqfft::step_radix2_domain<LFr> dom(m);
+    vector<LFr> v = load_fr(a, m);
+    dom.divide_by_Z_on_coset(v);
+    for (size_t i = 0; i < m; i++) store_fr(a + 4 * i, v[i]);
     return 0;
 }
 

@@ -252,6 +252,53 @@ def test_scalar_sum_identity_at_scale(engine, orc, grp, log2n):
     key.close()
 
 
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+@pytest.mark.parametrize("levels", [1, 2])
+def test_batch_affine_levels(engine, orc, golden, grp, levels):
+    """Batch-affine accumulation (pair_kernels.cuh): `levels` tree levels of affine pair additions with shared
+    inversions in front of the XYZZ tail must give the same group element as the plain path: every edge-case
+    fixture under forced geometries (buckets of 0, 1, 2, 3, ... entries; repeated bases -> tangent case, P / -P
+    pairs -> zero, zero bases), skewed scalars with hot buckets, a precomputed key, and the pipelined upload."""
+    g = golden(f"msm_{grp}")
+    n = 5000 if grp == "g1" else 1500
+    P, k = inputs.bases(orc, grp, n, seed=801, affine=False)
+    P[7] = P[6]
+    P[9] = inputs.negate(orc, grp, P[8:9])[0]
+    P[11] = inputs.zero_point(grp)
+    s = inputs.fr_uniform(orc, n, seed=802)
+    s[6:10] = s[6]  # equal scalars on the repeated / opposite bases: they meet in the same buckets
+    cases = {"uniform": s, "heavy01": inputs.fr_zero_one_heavy(orc, n, seed=803), "32bit": inputs.fr_small(n, 32),
+             "equal": np.tile(s[3], (n, 1))}
+    want = {name: orc.msm(grp, P, v, chunks=orc.max_threads(), variant=1) for name, v in cases.items()}
+    key = engine.CommitmentKey(grp, P)
+    try:
+        engine.set_tuning_ex("batch_affine", levels)
+        for c, L in ((0, 0), (3, 32), (6, 0), (9, 64), (13, 0)):
+            engine.set_tuning(c, L)
+            for name, v in cases.items():
+                assert (key.multi_exp(v) == want[name]).all(), (grp, levels, c, L, name)
+            if c:
+                for name in g["names"]:
+                    B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
+                    assert (engine.multi_exp(grp, B, S) == R).all(), (grp, levels, name, c, L)
+        engine.set_tuning(0, 0)
+        engine.set_pipeline_chunks(3)
+        assert (engine.multi_exp(grp, P, cases["uniform"]) == want["uniform"]).all(), "chunks"
+        engine.set_pipeline_chunks(0)
+        key.precompute(9)
+        engine.set_tuning_ex("use_precomputed", 2)
+        for name, v in cases.items():
+            assert (key.multi_exp(v) == want[name]).all(), (grp, levels, "precomputed", name)
+        assert (key.multi_exp(cases["uniform"][: n // 2 + 3], offset=17) ==
+                orc.msm(grp, P[17:17 + n // 2 + 3], cases["uniform"][: n // 2 + 3], chunks=orc.max_threads())).all()
+    finally:
+        engine.set_tuning_ex("batch_affine", 0)
+        engine.set_tuning_ex("use_precomputed", 1)
+        engine.set_tuning(0, 0)
+        engine.set_pipeline_chunks(0)
+        key.close()
+
+
 def _device_bases(engine, orc, grp, k):
     """P_i = k_i G made by the GPU fixed-base path, spot-checked against the oracle."""
     n = len(k)

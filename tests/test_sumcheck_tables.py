@@ -53,7 +53,82 @@ def test_oracle_vs_reference_live(orc, ref):
         assert (orc.fr_matrix_mle(A, rho) == ref.fr_matrix_mle(A, rho)).all()
 
 
+def test_oracle_step_domain_vs_reference_fixtures(orc, golden):
+    """libfqfft's step_radix2_domain (the domain of 2^k + 2^r constraints: BASELINE.json configs[3] has 2^21 + 1)."""
+    g = golden("sumcheck")
+    g5 = ints_to_mont([5], R_ORDER)
+    for lb, ls in g["step_shapes"]:
+        lb, ls = int(lb), int(ls)
+        a = g[f"step_a_{lb}_{ls}"]
+        for mode in range(4):
+            assert (orc.fr_step_fft(a, lb, ls, mode, g5) == g[f"step_{lb}_{ls}_m{mode}"]).all(), (lb, ls, mode)
+
+
+def _step_divide_z_expected(a, lb, ls):
+    """step_radix2_domain::divide_by_Z_on_coset (step_radix2_domain.tcc:213-241) with Python integers."""
+    r = R_ORDER
+    big, small = 1 << lb, 1 << ls
+    rou = 19103219067921713944291392827692070036145651957329286315305642004821462161904  # Fr::root_of_unity, order 2^28
+    omega = pow(rou, 1 << (28 - (lb + 1)), r)
+    coset = 5
+    Z0 = (pow(coset, big, r) - 1) % r
+    c1, c0, ratio = pow(coset, small, r) * Z0 % r, pow(omega, small, r) * Z0 % r, pow(omega, 2 * small, r)
+    Z1 = (pow(coset * omega, big, r) - 1) * (pow(coset * omega, small, r) - pow(omega, small, r)) % r
+    ai = mont_to_ints(a, r)
+    out, elt = [], 1
+    for i in range(big):
+        out.append(ai[i] * pow((c1 * elt - c0) % r, -1, r) % r)
+        elt = elt * ratio % r
+    z1i = pow(Z1, -1, r)
+    out += [ai[big + i] * z1i % r for i in range(small)]
+    return ints_to_mont(out, r), (c1, ratio, c0, z1i)
+
+
+def test_step_divide_z_formula_vs_reference_fixtures(golden):
+    g = golden("sumcheck")
+    for lb, ls in g["step_shapes"]:
+        lb, ls = int(lb), int(ls)
+        want, _ = _step_divide_z_expected(g[f"step_a_{lb}_{ls}"], lb, ls)
+        assert (want == g[f"step_{lb}_{ls}_divz"]).all(), (lb, ls)
+
+
 # ---------------------------------------------------------------- GPU: parity through the C-ABI
+@pytest.mark.gpu
+def test_gpu_step_domain_fixtures(engine, golden):
+    g = golden("sumcheck")
+    g5 = ints_to_mont([5], R_ORDER)
+    for lb, ls in g["step_shapes"]:
+        lb, ls = int(lb), int(ls)
+        a = g[f"step_a_{lb}_{ls}"]
+        for mode in range(4):
+            assert (engine.fr_step_fft(a, lb, ls, mode, g5) == g[f"step_{lb}_{ls}_m{mode}"]).all(), (lb, ls, mode)
+        _, (c1, ratio, c0, z1i) = _step_divide_z_expected(a, lb, ls)
+        c = ints_to_mont([c1, ratio, c0, z1i], R_ORDER)
+        got = engine.scale_inv_geometric(a, 1 << lb, c[0], c[1], c[2], c[3])
+        assert (got == g[f"step_{lb}_{ls}_divz"]).all(), (lb, ls, "divide_by_Z_on_coset")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lb,ls", [(1, 0), (10, 0), (11, 10), (12, 5), (14, 0), (17, 3)])
+def test_gpu_step_domain_vs_oracle(engine, orc, lb, ls):
+    a = orc.sha512_rng_fr(3300 + lb, (1 << lb) + (1 << ls))
+    g = orc.sha512_rng_fr(3400 + lb, 1)
+    for mode in range(4):
+        assert (engine.fr_step_fft(a, lb, ls, mode, g) == orc.fr_step_fft(a, lb, ls, mode, g)).all(), (lb, ls, mode)
+
+
+@pytest.mark.gpu
+def test_gpu_step_domain_round_trip_at_scale(engine):
+    """2^21 + 1 points (the 128 x 128 matrix product): iFFT(FFT(a)) = a and icosetFFT(cosetFFT(a)) = a."""
+    lb, ls = 21, 0
+    m = (1 << lb) + 1
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 1 << 64, size=(m, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    g5 = ints_to_mont([5], R_ORDER)
+    assert (engine.fr_step_fft(engine.fr_step_fft(a, lb, ls, 0), lb, ls, 1) == a).all()
+    assert (engine.fr_step_fft(engine.fr_step_fft(a, lb, ls, 2, g5), lb, ls, 3, g5) == a).all()
+
 @pytest.mark.gpu
 def test_gpu_sumcheck_fixtures(engine, golden):
     g = golden("sumcheck")

@@ -56,6 +56,18 @@ def main():
         rho = ref.sha512_rng_fr(9500 + d, d)
         f[f"A_{d}"], f[f"mrho_{d}"] = A, rho
         f[f"matrix_mle_{d}"] = ref.fr_matrix_mle(A, rho)
+    # libfqfft's step_radix2_domain (2^k + 2^r points): the four transforms and divide_by_Z_on_coset
+    g5 = ints_to_mont([5], R_ORDER)  # Fr::multiplicative_generator: the coset of r1cs_to_qap_witness_map
+    shapes = [(2, 0), (3, 1), (5, 0), (7, 4), (11, 0)]
+    f["step_shapes"] = np.array(shapes)
+    for lb, ls in shapes:
+        m = (1 << lb) + (1 << ls)
+        a = ref.sha512_rng_fr(9600 + lb, m)
+        a[: min(m, 4)] = edge[: min(m, 4)]
+        f[f"step_a_{lb}_{ls}"] = a
+        for mode in range(4):
+            f[f"step_{lb}_{ls}_m{mode}"] = ref.fr_step_fft(a, lb, ls, mode, g5)
+        f[f"step_{lb}_{ls}_divz"] = ref.fr_step_divide_z(a, lb, ls)
     np.savez_compressed(OUT, **f)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
