@@ -149,19 +149,57 @@ static int sum_partials(const uint64_t *pts, size_t n, uint64_t *out)
     return B200_OK;
 }
 
+static int apply_tuning(const std::string &k, int value)
+{
+    const char *key = k.c_str();
+    if (k == "reduce_log_segment") g_tune_logS = value;       // -1 = model
+    else if (k == "reduce_split") g_tune_split = value;       // 0 = auto
+    else if (k == "use_precomputed") g_tune_pre = value;      // 0: ignore precomputed levels of a key
+    else if (k == "host_horner") g_tune_host_horner = value;  // 0: the device also weights and sums the per-job results of a one-window reduction
+    else if (k == "reduce_marginals") g_tune_marginals = value;  // 0: bit decomposition over all segments (round 1)
+    else if (k == "batch_affine") g_tune_ba = std::min(std::max(value, 0), 2);  // tree levels of affine pair additions before the XYZZ tail
+    else if (k == "partition_sort") g_tune_sort = value;     // 0: the round-1 global-atomics counting sort
+    else if (k == "ones_filter") g_tune_ones = value;         // 0: scalars equal to one go through the sort like any other
+    else return fail(B200_ERR_ARG, "unknown tuning key %s", key);
+    return B200_OK;
+}
+
+// B200_TUNE="key=value,key=value": tuning knobs of b200_set_tuning_ex for processes that cannot call it (the C++ drivers,
+// profiler runs); unknown keys make b200_init fail loudly.
+static int apply_env_tuning()
+{
+    const char *e = std::getenv("B200_TUNE");
+    if (!e || !*e) return B200_OK;
+    std::string s(e);
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t end = s.find(',', pos);
+        if (end == std::string::npos) end = s.size();
+        const std::string kv = s.substr(pos, end - pos);
+        const size_t eq = kv.find('=');
+        if (eq == std::string::npos) return fail(B200_ERR_ARG, "B200_TUNE: expected key=value, got %s", kv.c_str());
+        const int rc = apply_tuning(kv.substr(0, eq), std::atoi(kv.c_str() + eq + 1));
+        if (rc != B200_OK) return rc;
+        pos = end + 1;
+    }
+    return B200_OK;
+}
+
 extern "C" {
 
 int b200_init(int n_gpus)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    return init_devices(nullptr, n_gpus);
+    const int rc = init_devices(nullptr, n_gpus);
+    return rc == B200_OK ? apply_env_tuning() : rc;
 }
 
 int b200_init_devices(const int *device_ids, int n)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!device_ids || n <= 0) return fail(B200_ERR_ARG, "device list is empty");
-    return init_devices(device_ids, n);
+    const int rc = init_devices(device_ids, n);
+    return rc == B200_OK ? apply_env_tuning() : rc;
 }
 
 void b200_shutdown(void)
@@ -494,18 +532,9 @@ int b200_set_tuning_ex(const char *key, int value)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!key) return fail(B200_ERR_ARG, "null key");
-    const std::string k(key);
-    if (k == "reduce_log_segment") g_tune_logS = value;       // -1 = model
-    else if (k == "reduce_split") g_tune_split = value;       // 0 = auto
-    else if (k == "use_precomputed") g_tune_pre = value;      // 0: ignore precomputed levels of a key
-    else if (k == "host_horner") g_tune_host_horner = value;  // 0: the device also weights and sums the per-job results of a one-window reduction
-    else if (k == "reduce_marginals") g_tune_marginals = value;  // 0: bit decomposition over all segments (round 1)
-    else if (k == "batch_affine") g_tune_ba = std::min(std::max(value, 0), 2);  // tree levels of affine pair additions before the XYZZ tail
-    else if (k == "partition_sort") g_tune_sort = value;     // 0: the round-1 global-atomics counting sort
-    else if (k == "ones_filter") g_tune_ones = value;         // 0: scalars equal to one go through the sort like any other
-    else return fail(B200_ERR_ARG, "unknown tuning key %s", key);
-    return B200_OK;
+    return apply_tuning(key, value);
 }
+
 
 int b200_set_pipeline_chunks(int chunks)
 {
