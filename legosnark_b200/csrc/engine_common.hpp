@@ -91,6 +91,7 @@ struct Device {
     DevBuf cnt, off, cursor, toff, tile_sums, totals, entries, digits, meta, order, len_hist, len_cursor;
     // radix-partition sort (engine_sort.cu): standard-form scalars, (entry, bucket) pairs, per-partition counters
     DevBuf std_scalars, items, part;
+    DevBuf task_bucket;  // per task: its bucket | first-task flag (seeded accumulation of pipelined chunks)
     // batch-affine accumulation (pair_kernels.cuh): the points of tree levels 1 and 2
     DevBuf pa1, pa2;
     bool sort_attr_set = false;
@@ -120,7 +121,7 @@ struct Device {
         cudaSetDevice(id);
         DevBuf *all[] = {&scalars, &bases_jac, &bases_aff, &flags, &prefix, &cnt, &off, &cursor, &toff, &tile_sums, &totals,
                          &entries, &digits, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
-                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big, &std_scalars, &items, &part, &pa1, &pa2};
+                         &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big, &std_scalars, &items, &part, &pa1, &pa2, &task_bucket};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;

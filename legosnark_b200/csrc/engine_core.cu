@@ -1,5 +1,7 @@
 // engine_core.cu — lifecycle, shared state and the extern "C" surface declared in
 // include/b200_msm.h.  The per-group work is in engine_g1.cu / engine_g2.cu.
+#include <cstdlib>
+
 #include "engine_common.hpp"
 #include "field.cuh"
 #include "host_arith.hpp"
@@ -84,6 +86,11 @@ size_t libff_window_size(const size_t *tab, size_t num_scalars)
 int init_devices(const int *ids, int n)
 {
     if (g_init) return B200_OK;
+    // CUDA 12 loads a kernel's code at its first launch by default; with ~200 kernels (the Fq2 ones are large) that put
+    // tens of milliseconds into the first MSM / commit of a process (cplink's first commit: 26-45 ms against 15 ms on
+    // the host).  Loading the whole module at initialisation keeps first calls at steady-state cost.  An explicit
+    // CUDA_MODULE_LOADING in the environment wins.
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     int visible = 0;
     cudaError_t e = cudaGetDeviceCount(&visible);
     if (e != cudaSuccess || visible == 0)
@@ -114,6 +121,13 @@ int init_devices(const int *ids, int n)
             for (auto &e : D.ev_ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&D.ev_sync, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&D.ev_busy, cudaEventDisableTiming));
+            // buffers of the small-MSM / batch paths (n <= 4096: cplink, the sigma proofs and polynomial commitments of the
+            // sum-check gadgets) exist before the first call: no cudaMalloc / cudaHostAlloc inside it
+            D.scalars.ensure((size_t)4096 * 32);
+            D.bases_jac.ensure((size_t)4096 * 192);
+            D.window_sums.ensure((size_t)64 * 256);
+            D.totals.ensure(32);
+            D.ensure_pinned((size_t)64 * 256 + 1024);
         }
     } catch (const CudaError &e2) {
         g_devs.clear();

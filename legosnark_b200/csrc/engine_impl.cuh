@@ -229,6 +229,7 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     D.digits.ensure((size_t)g.W * ((chunk_max + 3) & ~(size_t)3) * 4);
     D.meta.ensure(P.max_tasks * sizeof(uint2));
     D.order.ensure(P.max_tasks * 4);
+    D.task_bucket.ensure(P.max_tasks * 4);
     D.len_hist.ensure((size_t)(g.L + 1) * 4);
     D.len_cursor.ensure((size_t)(g.L + 1) * 4);
     D.partial.ensure(P.max_tasks * sizeof(XYZZ<F>));
@@ -259,7 +260,7 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
 // bucket sort of the digits of `n` scalars and accumulation of the bucket (task) sums into D.partial
 template <class F>
 void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const Affine<F> *d_aff, const uint8_t *d_flags,
-                             const Fr *d_scalars, size_t n, bool first_chunk = true)
+                             const Fr *d_scalars, size_t n, bool first_chunk = true, bool seeded = false)
 {
     const MsmGeom &g = P.g;
     SortGeom sg;
@@ -291,10 +292,12 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
     LAUNCH(D, k_scan_apply, P.ntiles, SCAN_THREADS, 0, st, cnt, g.NB, g.L, tile_sums, off, cursor, toff);
     LAUNCH(D, k_digit_scatter, dim3(cdiv(n, 1024), g.W), 256, 0, st, D.digits.as<uint32_t>(), n, dstride, g, cursor, entries);
     const uint32_t tblocks = cdiv(max_tasks, 256);
-    LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist, split, big);
+    LAUNCH(D, k_task_meta, tblocks, 256, (g.L + 1) * 4, st, cnt, off, toff, totals, g, meta, len_hist, split, big, D.task_bucket.as<uint32_t>());
     LAUNCH(D, k_len_scan, 1, 1024, 0, st, len_hist, len_cursor, g.L);
     LAUNCH(D, k_task_order, tblocks, 256, 2 * (g.L + 1) * 4, st, meta, totals, g, len_cursor, order);
     }
+    const uint32_t *tbk = D.task_bucket.as<uint32_t>();
+    const XYZZ<F> *seed = seeded ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr;  // chunk > 0 of a pipelined MSM
     CK(cudaEventRecord(D.ev[2], st));
     if (part_sort && ba) {
         // levels of independent affine pair additions with shared inversions, then the XYZZ tail (pair_kernels.cuh)
@@ -312,9 +315,9 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
             last = D.pa2.as<Affine<F>>();
         }
         LAUNCH(D, (k_accumulate_pa<F>), cdiv(max_tasks, 128), 128, 0, st, last, ba, (const uint2 *)meta, (const uint32_t *)order,
-               (const uint32_t *)totals, partial);
+               (const uint32_t *)totals, partial, tbk, seed);
     } else {
-        LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial);
+        LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk, seed);
     }
     CK(cudaEventRecord(D.ev[3], st));
     LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 8, 128, 0, st, cnt, toff, split, totals, g, partial);
@@ -336,7 +339,7 @@ template <class F>
 void enqueue_fold(Device &D, cudaStream_t st, const MsmPlan &P, bool first)
 {
     LAUNCH(D, (k_bucket_fold<F>), cdiv(P.g.NB, 128), 128, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(), D.partial.as<XYZZ<F>>(),
-           P.g.NB, first, D.bucket_sum.as<XYZZ<F>>());
+           P.g.NB, first, !first, D.bucket_sum.as<XYZZ<F>>());
 }
 
 // window reduction + D2H of the W window sums (and the entry / task totals of the last sort)
@@ -422,7 +425,7 @@ MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *
         CK(cudaStreamWaitEvent(st, D.ev_ready[j], 0));
         run_ingest<F, false>(D, st, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
         enqueue_sort_accumulate<F>(D, st, P, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, D.scalars.as<Fr>() + lo,
-                                   cnt, j == 0);
+                                   cnt, j == 0, j > 0);
         enqueue_fold<F>(D, st, P, j == 0);
     }
     enqueue_reduce<F>(D, st, P, true);

@@ -68,7 +68,7 @@ void enqueue_partition_sort(Device &D, cudaStream_t st, const MsmGeom &g, const 
            (const uint32_t *)len_hist, len_cursor, g.L, 0u, 0u, (uint32_t *)nullptr);
     LAUNCH(D, k_task_emit, sg.NP, FINE_THREADS, task_emit_smem(sg, g.L), st, (const uint32_t *)D.cnt.as<uint32_t>(),
            (const uint32_t *)D.off.as<uint32_t>(), (const uint32_t *)ptstart, g, sg, D.toff.as<uint32_t>(), D.meta.as<uint2>(),
-           D.order.as<uint32_t>(), totals, D.split.as<uint32_t>(), D.big.as<uint32_t>(), len_cursor);
+           D.order.as<uint32_t>(), totals, D.split.as<uint32_t>(), D.big.as<uint32_t>(), len_cursor, D.task_bucket.as<uint32_t>());
 }
 
 }  // namespace eng

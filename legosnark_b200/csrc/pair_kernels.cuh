@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_add(const Affine<F> *__re
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate_pa(const Affine<F> *__restrict__ pa, uint32_t levels, const uint2 *__restrict__ meta,
                                                         const uint32_t *__restrict__ order, const uint32_t *__restrict__ totals,
-                                                        XYZZ<F> *__restrict__ partial)
+                                                        XYZZ<F> *__restrict__ partial, const uint32_t *__restrict__ task_bucket,
+                                                        const XYZZ<F> *__restrict__ seed)
 {
     const uint32_t ntasks = totals[1];
     const uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,6 +190,10 @@ __global__ void __launch_bounds__(128) k_accumulate_pa(const Affine<F> *__restri
     const Affine<F> *src = pa + (m.x >> levels);
     const uint32_t cnt = (m.y + (1u << levels) - 1) >> levels;
     XYZZ<F> acc = XYZZ<F>::inf();
+    if (seed) {
+        const uint32_t tb = task_bucket[t];
+        if (tb >> 31) acc = seed[tb & 0x7fffffffu];
+    }
     if (sizeof(F) <= 32) {  // G1: next point in registers during the addition; G2: no room (see k_accumulate)
         Affine<F> p = src[0];
         for (uint32_t k = 0; k < cnt; k++) {

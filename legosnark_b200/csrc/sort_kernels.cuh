@@ -334,7 +334,7 @@ static __global__ void __launch_bounds__(FINE_THREADS) k_task_emit(const uint32_
                                                                     uint32_t *__restrict__ toff, uint2 *__restrict__ meta,
                                                                     uint32_t *__restrict__ order, uint32_t *__restrict__ totals,
                                                                     uint32_t *__restrict__ split, uint32_t *__restrict__ big,
-                                                                    uint32_t *__restrict__ len_cursor)
+                                                                    uint32_t *__restrict__ len_cursor, uint32_t *__restrict__ task_bucket)
 {
     extern __shared__ uint32_t sh[];
     __shared__ uint32_t tmp[33];
@@ -385,6 +385,7 @@ static __global__ void __launch_bounds__(FINE_THREADS) k_task_emit(const uint32_
         const uint32_t rem = cs[b] - j * L;
         const uint32_t len = rem < L ? rem : L;
         meta[t0 + t] = make_uint2(os[b] + j * L, len);
+        task_bucket[t0 + t] = (b0 + b) | (j == 0 ? 0x80000000u : 0u);
         order[lstart[len] + atomicAdd(&lh[len], 1u)] = t0 + t;
     }
 }
