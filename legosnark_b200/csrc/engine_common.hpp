@@ -229,6 +229,7 @@ void for_each_shard(size_t nshards, Fn fn)
 
 // per-group entry points: templates defined in engine_impl.cuh, explicitly
 // instantiated for Fq in engine_g1.cu and for Fq2 in engine_g2.cu
+template <class F> void preload_small_path();
 template <class F> int msm_host(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out);
 template <class F> int msm_batch(const uint64_t *bases, const uint64_t *scalars, const uint64_t *offsets, size_t count, uint64_t *out);
 template <class F> int pin_bases(const uint64_t *bases, const void *d_affine, size_t n, uint64_t *handle);

@@ -86,11 +86,6 @@ size_t libff_window_size(const size_t *tab, size_t num_scalars)
 int init_devices(const int *ids, int n)
 {
     if (g_init) return B200_OK;
-    // CUDA 12 loads a kernel's code at its first launch by default; with ~200 kernels (the Fq2 ones are large) that put
-    // tens of milliseconds into the first MSM / commit of a process (cplink's first commit: 26-45 ms against 15 ms on
-    // the host).  Loading the whole module at initialisation keeps first calls at steady-state cost.  An explicit
-    // CUDA_MODULE_LOADING in the environment wins.
-    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     int visible = 0;
     cudaError_t e = cudaGetDeviceCount(&visible);
     if (e != cudaSuccess || visible == 0)
@@ -128,6 +123,8 @@ int init_devices(const int *ids, int n)
             D.window_sums.ensure((size_t)64 * 256);
             D.totals.ensure(32);
             D.ensure_pinned((size_t)64 * 256 + 1024);
+            preload_small_path<Fq>();
+            preload_small_path<Fq2>();
         }
     } catch (const CudaError &e2) {
         g_devs.clear();

@@ -1095,7 +1095,25 @@ int test_group_op(int op, const uint64_t *a, const uint64_t *b, size_t n, uint32
     return run_elementwise<Jacobian<F>>(a, b, n, out, GroupOp<F>{op, k, b != nullptr});
 }
 
+// CUDA 12 loads a kernel's code at its first launch; the small-path kernels (n <= 4096: cplink's commits and prove, the
+// sigma proofs and polynomial commitments of the sum-check gadgets) are queried once at initialisation so that the first
+// small MSM of a process runs at steady-state cost (cplink's first commit: 26-45 ms -> 2.7 ms) without loading all ~200
+// kernels eagerly (that costs ~0.9 s of start-up).
+template <class F>
+void preload_small_path()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_msm_small<F, Jacobian<F>>);
+    cudaFuncGetAttributes(&a, k_msm_small<F, Affine<F>>);
+    cudaFuncGetAttributes(&a, k_ingest<F, false>);
+    cudaFuncGetAttributes(&a, k_ingest<F, true>);
+    cudaFuncGetAttributes(&a, k_batch_terms<F>);
+    cudaFuncGetAttributes(&a, k_batch_sums<F>);
+    cudaGetLastError();
+}
+
 #define B200_INSTANTIATE_GROUP(F)                                                                                       \
+    template void preload_small_path<F>();                                                                              \
     template int msm_host<F>(const uint64_t *, const uint64_t *, size_t, uint64_t *);                                   \
     template int msm_batch<F>(const uint64_t *, const uint64_t *, const uint64_t *, size_t, uint64_t *);                \
     template int pin_bases<F>(const uint64_t *, const void *, size_t, uint64_t *);                                      \
