@@ -257,6 +257,18 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     return P;
 }
 
+// two lanes per task for G2 (k_accumulate_g2pair); the Fq overload is never called (sizeof(F) == 64 guards the call site)
+inline void launch_accumulate_g2pair(Device &D, cudaStream_t st, const Affine<Fq2> *d_aff, const uint32_t *entries, const uint2 *meta,
+                                     const uint32_t *order, const uint32_t *totals, XYZZ<Fq2> *partial, const uint32_t *tbk,
+                                     const XYZZ<Fq2> *seed, size_t max_tasks)
+{
+    LAUNCH(D, k_accumulate_g2pair, cdiv(max_tasks, 64), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk, seed);
+}
+inline void launch_accumulate_g2pair(Device &, cudaStream_t, const Affine<Fq> *, const uint32_t *, const uint2 *, const uint32_t *,
+                                     const uint32_t *, XYZZ<Fq> *, const uint32_t *, const XYZZ<Fq> *, size_t)
+{
+}
+
 // bucket sort of the digits of `n` scalars and accumulation of the bucket (task) sums into D.partial
 template <class F>
 void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const Affine<F> *d_aff, const uint8_t *d_flags,
@@ -316,6 +328,8 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
         }
         LAUNCH(D, (k_accumulate_pa<F>), cdiv(max_tasks, 128), 128, 0, st, last, ba, (const uint2 *)meta, (const uint32_t *)order,
                (const uint32_t *)totals, partial, tbk, seed);
+    } else if (sizeof(F) == 64 && g_tune_g2pair) {
+        launch_accumulate_g2pair(D, st, d_aff, entries, meta, order, totals, partial, tbk, seed, max_tasks);
     } else {
         LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk, seed);
     }

@@ -566,6 +566,137 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict_
 }
 
 // ------------------------------------------------------------------------------
+// G2: two lanes per task.  One thread per task needs the whole XYZZ<Fq2> accumulator (64 registers), a point (32) and the
+// product temporaries: 190 registers, two blocks per SM, and the multiply-add pipe idles on dependency stalls
+// (k_accumulate<Fq2>: 80 % of the IMAD bound).  Here lane 2i holds the c0 components and lane 2i+1 the c1 components of
+// task i's accumulator and operands ("half" elements): additions are component-wise, and a product
+//     (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + (a0 b1 + a1 b0) u
+// is ONE fused two-product Montgomery pass per lane (Fq::mul_add, 200 multiply-adds) after the partners swap their halves
+// with 16 shuffles: the same 400 multiply-adds as Fq2::mul, split over two lanes, with half the registers per lane.
+// All branches are uniform within a pair; shuffles name only the pair in their mask.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ Fq pair_swap(const Fq &a, uint32_t pmask)
+{
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(pmask, a.l[i], 1);
+    return r;
+}
+// own half of a * b
+__device__ __forceinline__ Fq h2_mul(const Fq &a, const Fq &b, uint32_t par, uint32_t pmask)
+{
+    const Fq pa = pair_swap(a, pmask), pb = pair_swap(b, pmask);
+    const Fq x1 = par ? pa : a;            // lane 0: a0 b0 + (-a1) b1;   lane 1: a0 b1 + a1 b0
+    const Fq x2 = par ? a : Fq::neg(pa);
+    return Fq::mul_add(x1, b, x2, pb);
+}
+// own half of a^2 (complex squaring, fp2.tcc:111-120): (a0 + a1)(a0 - a1) | 2 a0 a1
+__device__ __forceinline__ Fq h2_sqr(const Fq &a, uint32_t par, uint32_t pmask)
+{
+    const Fq pa = pair_swap(a, pmask);
+    const Fq u = par ? Fq::dbl(pa) : Fq::add(a, pa);
+    const Fq v = par ? a : Fq::sub(a, pa);
+    return Fq::mul(u, v);
+}
+__device__ __forceinline__ bool h2_is_zero(const Fq &a, uint32_t pmask)
+{
+    const int z = a.is_zero() ? 1 : 0;
+    return z && __shfl_xor_sync(pmask, z, 1);
+}
+__device__ __forceinline__ Fq2 h2_full(const Fq &a, uint32_t par, uint32_t pmask)
+{
+    const Fq pa = pair_swap(a, pmask);
+    return par ? Fq2{pa, a} : Fq2{a, pa};
+}
+__device__ __forceinline__ Fq h2_own(const Fq2 &a, uint32_t par) { return par ? a.c1 : a.c0; }
+
+struct HalfXYZZ {
+    Fq x, y, zz, zzz;
+};
+
+// acc += (x2, +-y2), madd-2008-s on half elements; same case analysis as xyzz_madd
+__device__ __forceinline__ void h2_madd(HalfXYZZ &acc, const Fq &x2, const Fq &y2_in, bool negate, uint32_t par, uint32_t pmask)
+{
+    const Fq y2 = Fq::cneg(y2_in, negate);
+    if (h2_is_zero(acc.zz, pmask)) {
+        acc.x = x2;
+        acc.y = y2;
+        acc.zz = acc.zzz = par ? Fq::zero() : Fq::one();
+        return;
+    }
+    const Fq U2 = h2_mul(x2, acc.zz, par, pmask);
+    const Fq S2 = h2_mul(y2, acc.zzz, par, pmask);
+    const Fq P = Fq::sub(U2, acc.x);
+    const Fq R = Fq::sub(S2, acc.y);
+    if (h2_is_zero(P, pmask)) {
+        if (h2_is_zero(R, pmask)) {  // same point: both lanes double the full point and keep their half (rare)
+            const XYZZ<Fq2> d = xyzz_dbl_affine<Fq2>(h2_full(x2, par, pmask), h2_full(y2, par, pmask));
+            acc.x = h2_own(d.x, par);
+            acc.y = h2_own(d.y, par);
+            acc.zz = h2_own(d.zz, par);
+            acc.zzz = h2_own(d.zzz, par);
+        } else {
+            acc.x = acc.y = acc.zz = acc.zzz = Fq::zero();
+        }
+        return;
+    }
+    const Fq PP = h2_sqr(P, par, pmask);
+    const Fq PPP = h2_mul(P, PP, par, pmask);
+    const Fq Q = h2_mul(acc.x, PP, par, pmask);
+    const Fq X3 = Fq::sub(Fq::sub(h2_sqr(R, par, pmask), PPP), Fq::dbl(Q));
+    acc.y = Fq::sub(h2_mul(R, Fq::sub(Q, X3), par, pmask), h2_mul(acc.y, PPP, par, pmask));
+    acc.x = X3;
+    acc.zz = h2_mul(acc.zz, PP, par, pmask);
+    acc.zzz = h2_mul(acc.zzz, PPP, par, pmask);
+}
+
+// k_accumulate for G2 with two lanes per task (64 tasks per 128-thread block)
+static __global__ void __launch_bounds__(128, 4) k_accumulate_g2pair(const Affine<Fq2> *__restrict__ bases, const uint32_t *__restrict__ entries,
+                                                                   const uint2 *__restrict__ meta, const uint32_t *__restrict__ order,
+                                                                   const uint32_t *__restrict__ totals, XYZZ<Fq2> *__restrict__ partial,
+                                                                   const uint32_t *__restrict__ task_bucket, const XYZZ<Fq2> *__restrict__ seed)
+{
+    const uint32_t ntasks = totals[1];
+    const uint32_t gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    if (gidx >= ntasks) return;  // both lanes of a pair leave together
+    const uint32_t lane = threadIdx.x & 31u, par = lane & 1u, pmask = 3u << (lane & ~1u);
+    const uint32_t t = order[gidx];
+    const uint2 m = meta[t];
+    const uint32_t *e = entries + m.x;
+    HalfXYZZ acc;
+    acc.x = acc.y = acc.zz = acc.zzz = Fq::zero();
+    if (seed) {
+        const uint32_t tb = task_bucket[t];
+        if (tb >> 31) {
+            const Fq *sp = reinterpret_cast<const Fq *>(seed + (tb & 0x7fffffffu));  // x.c0 x.c1 y.c0 y.c1 zz.c0 zz.c1 zzz.c0 zzz.c1
+            acc.x = sp[par];
+            acc.y = sp[2 + par];
+            acc.zz = sp[4 + par];
+            acc.zzz = sp[6 + par];
+        }
+    }
+    uint32_t cur = e[0];
+    const Fq *bp = reinterpret_cast<const Fq *>(bases + (cur & 0x7fffffffu));  // x.c0 x.c1 y.c0 y.c1
+    Fq px = bp[par], py = bp[2 + par];
+    for (uint32_t k = 0; k < m.y; k++) {
+        const uint32_t neg = cur >> 31;
+        const Fq qx = px, qy = py;
+        if (k + 1 < m.y) {
+            cur = e[k + 1];
+            bp = reinterpret_cast<const Fq *>(bases + (cur & 0x7fffffffu));
+            px = bp[par];
+            py = bp[2 + par];
+        }
+        h2_madd(acc, qx, qy, neg != 0, par, pmask);
+    }
+    Fq *op = reinterpret_cast<Fq *>(partial + t);
+    op[par] = acc.x;
+    op[2 + par] = acc.y;
+    op[4 + par] = acc.zz;
+    op[6 + par] = acc.zzz;
+}
+
+// ------------------------------------------------------------------------------
 // warp-level helpers on XYZZ values
 // ------------------------------------------------------------------------------
 template <class F>
