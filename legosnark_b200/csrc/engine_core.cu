@@ -32,7 +32,7 @@ std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1, g_tune_host_horner = 1;
-int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 1;
+int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 0;
 bool g_scalars_resident = false;
 
 static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal

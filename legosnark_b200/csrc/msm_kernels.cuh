@@ -601,7 +601,8 @@ __device__ __forceinline__ Fq h2_sqr(const Fq &a, uint32_t par, uint32_t pmask)
 __device__ __forceinline__ bool h2_is_zero(const Fq &a, uint32_t pmask)
 {
     const int z = a.is_zero() ? 1 : 0;
-    return z && __shfl_xor_sync(pmask, z, 1);
+    const int o = __shfl_xor_sync(pmask, z, 1);  // both lanes of the pair always execute the shuffle (no short-circuit)
+    return (z & o) != 0;
 }
 __device__ __forceinline__ Fq2 h2_full(const Fq &a, uint32_t par, uint32_t pmask)
 {

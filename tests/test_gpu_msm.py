@@ -299,6 +299,47 @@ def test_batch_affine_levels(engine, orc, golden, grp, levels):
         key.close()
 
 
+def test_g2_lane_pairs(engine, orc, golden):
+    """k_accumulate_g2pair (two lanes per G2 task, the halves of every Fq2 value on neighbouring lanes): same group element
+    as the one-thread-per-task kernel on the edge-case fixtures under forced geometries (repeated bases -> the tangent
+    branch runs on full elements inside the pair, P / -P -> zero), skewed scalars, a precomputed key and pipelined chunks."""
+    g = golden("msm_g2")
+    n = 2500
+    P, _ = inputs.bases(orc, "g2", n, seed=821, affine=False)
+    P[7] = P[6]
+    P[9] = inputs.negate(orc, "g2", P[8:9])[0]
+    P[11] = inputs.zero_point("g2")
+    s = inputs.fr_uniform(orc, n, seed=822)
+    s[6:10] = s[6]
+    cases = {"uniform": s, "heavy01": inputs.fr_zero_one_heavy(orc, n, seed=823), "equal": np.tile(s[3], (n, 1))}
+    want = {name: orc.msm("g2", P, v, chunks=orc.max_threads(), variant=1) for name, v in cases.items()}
+    key = engine.CommitmentKey("g2", P)
+    try:
+        engine.set_tuning_ex("g2_lane_pairs", 1)
+        for c, L in ((0, 0), (4, 32), (9, 0), (12, 64)):
+            engine.set_tuning(c, L)
+            for name, v in cases.items():
+                assert (key.multi_exp(v) == want[name]).all(), (c, L, name)
+            if c:
+                for name in g["names"]:
+                    B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
+                    assert (engine.multi_exp("g2", B, S) == R).all(), (name, c, L)
+        engine.set_tuning(0, 0)
+        engine.set_pipeline_chunks(3)
+        assert (engine.multi_exp("g2", P, cases["uniform"]) == want["uniform"]).all(), "chunks"
+        engine.set_pipeline_chunks(0)
+        key.precompute(8)
+        engine.set_tuning_ex("use_precomputed", 2)
+        for name, v in cases.items():
+            assert (key.multi_exp(v) == want[name]).all(), ("precomputed", name)
+    finally:
+        engine.set_tuning_ex("g2_lane_pairs", 0)
+        engine.set_tuning_ex("use_precomputed", 1)
+        engine.set_tuning(0, 0)
+        engine.set_pipeline_chunks(0)
+        key.close()
+
+
 def _device_bases(engine, orc, grp, k):
     """P_i = k_i G made by the GPU fixed-base path, spot-checked against the oracle."""
     n = len(k)
