@@ -87,11 +87,14 @@ inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride
 }
 
 // window bits for extending a key of n bases (b200_key_precompute_*), from the sweeps in
-// profiles/r09d_precompute_sweep_2p*.jsonl: c = 17 (255 = 15 x 17: a full top window) up to 2^18, 20 up
-// to 2^24, 22 beyond (the 2^21 buckets only pay off when W * n additions dominate).
+// profiles/r09d_precompute_sweep_2p*.jsonl and profiles/r2j_precompute_window_sweep.jsonl: c = 17 (255 = 15 x 17: a full top
+// window) up to 2^18, 20 beyond.  Round 1 switched to c = 22 from 2^25 on; measured in round 2 that geometry loses at every
+// size (2^24: 38.2 vs 35.7 ms; 2^26: 457 vs ~145 ms, profiles/r2p_identity_check.log, r2q_stage.jsonl): its top window holds
+// 12 bits, so n / 3097 entries pile onto each of the lowest 3097 buckets.  c = 20 needs 13 n < 2^31 table entries (n <= 2^27).
 inline uint32_t choose_precompute_window(size_t n)
 {
-    return n < ((size_t)1 << 19) ? 17 : n < ((size_t)1 << 25) ? 20 : 22;
+    if (n < ((size_t)1 << 19)) return 17;
+    return (size_t)13 * n < ((size_t)1 << 31) ? 20 : 22;
 }
 // a (sub-)range of a precomputed key takes the precomputed path when it fills the one big bucket set to
 // at least ~4 entries per bucket; shorter ranges run on the plain level-0 bases

@@ -13,7 +13,9 @@
 // read (the caller may reuse it), and `st` is ordered after the data has landed; d2h() returns when
 // the destination holds the data.
 #pragma once
+#include <condition_variable>
 #include <cstdlib>
+#include <functional>
 
 #include "engine_common.hpp"
 
@@ -73,6 +75,67 @@ struct Stager {
 
 Stager &stager_of(Device &D);  // engine_core.cu: one per device, created on first use, freed at shutdown
 
+// The staging threads are kept between transfers: a pipelined host-buffer MSM stages eight transfers per call (scalars
+// and bases of four upload chunks), and starting four fresh std::threads for each of them cost more than 1 ms of the
+// 9 ms call.  run(n, fn) executes fn(0) .. fn(n-1) on the pool's threads and returns when all have finished.
+class CopyPool {
+  public:
+    static CopyPool &get()
+    {
+        static CopyPool pool;
+        return pool;
+    }
+    void run(int n, const std::function<void(int)> &fn)
+    {
+        std::lock_guard<std::mutex> one_at_a_time(run_mu_);  // in-process multi-GPU: the per-device host threads take turns
+        std::unique_lock<std::mutex> lk(mu_);
+        while ((int)workers_.size() < n) {
+            const int id = (int)workers_.size();
+            workers_.emplace_back([this, id] { loop(id); });
+        }
+        fn_ = &fn;
+        want_ = n;
+        pending_ = n;
+        generation_++;
+        cv_work_.notify_all();
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            cv_work_.notify_all();
+        }
+        for (auto &t : workers_) t.join();
+    }
+
+  private:
+    void loop(int id)
+    {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_work_.wait(lk, [&] { return stop_ || (generation_ != seen && id < want_); });
+            if (stop_) return;
+            seen = generation_;
+            const std::function<void(int)> *fn = fn_;
+            lk.unlock();
+            (*fn)(id);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int want_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
 inline bool is_pageable(const void *p)
 {
     cudaPointerAttributes a;
@@ -91,12 +154,10 @@ inline void staged_copy(Device &D, void *dst, const void *src, size_t bytes, cud
     // the private streams start after whatever `st` still has in flight on these buffers
     CK(cudaEventRecord(S.gate, st));
     const size_t nchunks = (bytes + COPY_CHUNK - 1) / COPY_CHUNK;
-    std::vector<std::thread> th;
     const int COPY_THREADS = copy_threads();
     std::vector<std::string> errs(COPY_THREADS);
     const int dev_id = D.id;
-    for (int t = 0; t < COPY_THREADS; t++)
-        th.emplace_back([&, t] {
+    CopyPool::get().run(COPY_THREADS, [&](int t) {
             try {
                 CK(cudaSetDevice(dev_id));
                 CK(cudaStreamWaitEvent(S.cs[t], S.gate, 0));
@@ -130,9 +191,10 @@ inline void staged_copy(Device &D, void *dst, const void *src, size_t bytes, cud
                 CK(cudaEventRecord(S.done[t], S.cs[t]));
             } catch (const CudaError &e) {
                 errs[t] = e.msg;
+            } catch (...) {
+                errs[t] = "host error in a staging thread";
             }
         });
-    for (auto &x : th) x.join();
     for (auto &e : errs)
         if (!e.empty()) throw CudaError{e};
     for (int t = 0; t < COPY_THREADS; t++) CK(cudaStreamWaitEvent(st, S.done[t], 0));

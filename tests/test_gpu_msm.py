@@ -380,8 +380,9 @@ def test_scalar_sum_identity_config5_sizes(engine, orc, grp, log2n):
 
 @pytest.mark.parametrize("grp,log2n", [("g1", 15), ("g2", 13)])
 def test_precomputed_window_22(engine, orc, grp, log2n):
-    """choose_precompute_window picks c = 22 from 2^25 bases on (12 levels, 2^21 buckets); that geometry is run
-    here on a key small enough for the driver's suite, forced through b200_key_precompute_*(22)."""
+    """c = 22 (12 levels, 2^21 buckets) is the precomputed geometry for keys beyond 2^27 bases (13 n >= 2^31) and the
+    widest one the partition sort handles; it is run here on a key small enough for the driver's suite, forced through
+    b200_key_precompute_*(22)."""
     n = 1 << log2n
     k = inputs.fr_uniform(orc, n, seed=611)
     P = _device_bases(engine, orc, grp, k)
