@@ -272,12 +272,24 @@ def main():
     n_total = world * n if args.scaling == "weak" else 1 << args.log2n
     mailbox = None
     if world > 1 and args.transport == "mailbox":
+        # one node: the ranks share /dev/shm.  If it cannot be used (read-only, missing) every rank falls back to the
+        # torch.distributed transport together (the flag is agreed on with an all_reduce).
         name = f"b200_partials_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'run')}"
-        if rank == 0:
-            mailbox = multi.HostMailbox(name, rank, world, create=True)
-        dist.barrier()
-        if rank != 0:
-            mailbox = multi.HostMailbox(name, rank, world, create=False)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            if rank == 0:
+                mailbox = multi.HostMailbox(name, rank, world, create=True)
+        except OSError:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) and rank != 0:
+            try:
+                mailbox = multi.HostMailbox(name, rank, world, create=False)
+            except OSError:
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok[0]):
+            mailbox = None
     L = 12 if group == "g1" else 24
     A = 8 if group == "g1" else 16
     stream = torch.cuda.current_stream().cuda_stream

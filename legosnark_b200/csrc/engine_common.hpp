@@ -177,6 +177,7 @@ extern b200_stats_t g_stats;
 extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre, g_tune_ones, g_tune_host_horner;
 extern int g_tune_marginals;  // 1: one-window reduction by marginal sums (measured: no faster, profiles/r2c); 0 (default): bit decomposition over all segments
 extern int g_tune_g2pair;  // 1: G2 accumulation with two lanes per task (measured 5 % slower: profiles/r2n_g2_lane_pairs.jsonl); 0 (default): one thread per task
+extern int g_tune_even_chunks;  // 1 (default): equal upload chunks; 0: short first chunk (measured: no gain)
 extern int g_tune_ba;    // batch-affine tree levels in front of the XYZZ accumulation: 0 (off), 1 or 2
 extern int g_tune_sort;  // 1 (default): radix partition staged through shared memory; 0: round-1 global-atomics counting sort
 // set while the second MSM of a knowledge-commitment pair runs: every device still holds the

@@ -17,8 +17,10 @@ P = torch.from_numpy(lb.batch_exp_once("g1", generator("g1"), k).view(np.int64))
 s = torch.from_numpy(random_scalars(n, 1).view(np.int64)).pin_memory().numpy().view(np.uint64)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ref = None
-for chunks in (0, 2, 4, 8):
-    for c in (0, 14, 15, 16, 17):
+for even in (1, 0):
+  lb.set_tuning_ex("even_chunks", even)
+  for chunks in ((0, 3, 4, 5, 6, 8) if not even else (0,)):
+    for c in (0,):
         lb.set_tuning(c, 0)
         lb.set_pipeline_chunks(chunks)
         ts = []
@@ -31,7 +33,7 @@ for chunks in (0, 2, 4, 8):
         if ref is None:
             ref = r
         st = lb.last_stats()
-        print(json.dumps({"log2n": log2n, "chunks": chunks, "c_forced": c, "c": st["window_bits"], "W": st["num_windows"],
+        print(json.dumps({"log2n": log2n, "even_chunks": even, "chunks": chunks, "c_forced": c, "c": st["window_bits"], "W": st["num_windows"],
                           "e2e_ms_median": float(np.median(ts[2:])), "e2e_ms_min": float(np.min(ts[2:])), "same": bool((r == ref).all())}), flush=True)
 lb.set_tuning(0, 0)
 lb.set_pipeline_chunks(0)
