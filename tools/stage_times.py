@@ -45,6 +45,8 @@ def main():
         for name, v in zip(names, combo):
             if name == "window_bits":
                 lb.set_tuning(v, 0)
+            elif name == "task_len":
+                lb.set_tuning(0, v)
             else:
                 lb.set_tuning_ex(name, v)
         rows = []
