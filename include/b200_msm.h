@@ -186,6 +186,18 @@ int b200_fr_mle_bind(const uint64_t *table /* 2 half x 4 */, size_t half, const 
  * host there) run on the device; one upload and one download per call. */
 int b200_fr_step_fft(uint64_t *a /* (2^log_big + 2^log_small) x 4 */, size_t log_big, size_t log_small, int mode, const uint64_t *coset_g);
 
+/* The vector part of libsnark's r1cs_to_qap_witness_map (SNK/reductions/r1cs_to_qap/r1cs_to_qap.tcc:232-311, SNK =
+ * depends/libsnark/libsnark) for d1 = d2 = d3 = 0, as every Groth16 prover calls it (r1cs_gg_ppzksnark.tcc:402-415): from the
+ * evaluations aA, aB, aC of the constraint polynomials on the domain to the coefficients of H = (A B - C) / Z --
+ * three iFFTs, three coset FFTs, the pointwise product and difference, divide_by_Z_on_coset and the inverse coset FFT --
+ * with ONE upload of the three vectors and one download; nothing returns to the host between the seven transforms.
+ * Domain: log_small == B200_QAP_BASIC: basic_radix2_domain of m = 2^log_big points, div_consts = {Z(g)^-1} (4 limbs);
+ * otherwise step_radix2_domain of m = 2^log_big + 2^log_small points, div_consts = {c1, ratio, c0, Z1^-1} (16 limbs) as in
+ * b200_fr_scale_inv_geometric.  H receives m elements (the caller appends coefficients_for_H[m] = 0). */
+#define B200_QAP_BASIC ((size_t)-1)
+int b200_qap_h_coefficients(const uint64_t *aA /* m x 4 */, const uint64_t *aB /* m x 4 */, const uint64_t *aC /* m x 4 */, size_t log_big,
+                            size_t log_small, const uint64_t coset_g[4], const uint64_t *div_consts, uint64_t *H /* m x 4 */);
+
 /* step_radix2_domain::divide_by_Z_on_coset (FQFFT/evaluation_domain/domains/step_radix2_domain.tcc:213-241; FQFFT =
  * depends/libsnark/depends/libfqfft/libfqfft): the domain libfqfft picks for 2^k + 2^r constraints (the 128 x 128 matrix
  * product of BASELINE.json configs[3]: 2^21 + 1) divides by Z with ONE FIELD INVERSION PER POINT on the host, 95 % of the

@@ -117,6 +117,20 @@ int main(int argc, char **argv)
     const bool ok = r1cs_gg_ppzksnark_verifier_strong_IC<ppT>(keypair.vk, pb.primary_input(), proof);
     const double verify_ms = now_ms() - t0;
 
+    // ---- parity of the witness map: the shim's split (host evaluation + b200_qap_h_coefficients) against the reference's own
+    // function body (still reachable as libsnark_cpu_r1cs_to_qap_witness_map), H coefficient by H coefficient ----
+    const char *wm_parity = "n/a";
+#ifdef B200_SHIM_R1CS_TO_QAP_HPP_
+    {
+        const qap_witness<FieldT> w_gpu = r1cs_to_qap_witness_map(keypair.pk.constraint_system, pb.primary_input(), pb.auxiliary_input(),
+                                                                   FieldT::zero(), FieldT::zero(), FieldT::zero());
+        const qap_witness<FieldT> w_ref = libsnark_cpu_r1cs_to_qap_witness_map(keypair.pk.constraint_system, pb.primary_input(),
+                                                                                pb.auxiliary_input(), FieldT::zero(), FieldT::zero(), FieldT::zero());
+        wm_parity = (w_gpu.coefficients_for_H == w_ref.coefficients_for_H && w_gpu.coefficients_for_ABCs == w_ref.coefficients_for_ABCs &&
+                     w_gpu.degree() == w_ref.degree()) ? "identical" : "MISMATCH";
+    }
+#endif
+
     // ---- parity of the prover's MSMs against the reference templates (b200 build only) ----
     const char *parity = "n/a";
 #ifdef B200_SHIM_MULTIEXP_HPP_
@@ -147,7 +161,7 @@ int main(int argc, char **argv)
     (void)res2;
     printf("{\"example\": \"groth16matrix\", \"impl\": \"%s\", \"n\": %d, \"constraints\": %zu, \"satisfied\": %s, "
            "\"circuit_ms\": %.1f, \"keygen_ms\": %.1f, \"snark_prove_ms\": %.1f, \"of_which_witness_map_ms\": %.1f, \"commit_msm_ms\": %.2f, \"prove_ms\": %.1f, "
-           "\"verify_ms\": %.2f, \"verified\": %s, \"parity\": \"%s\"}\n",
+           "\"verify_ms\": %.2f, \"verified\": %s, \"parity\": \"%s\", \"witness_map_parity\": \"%s\"}\n",
 #if defined(B200_SHIM_MULTIEXP_HPP_)
            "b200",
 #elif defined(MULTICORE)
@@ -156,6 +170,6 @@ int main(int argc, char **argv)
            "libff-cpu",
 #endif
            n, constraints, sat ? "true" : "false", circuit_ms, keygen_ms, snark_prove_ms, witness_map_ms, commit_ms, snark_prove_ms + commit_ms,
-           verify_ms, ok ? "true" : "false", parity);
-    return (ok && sat && strcmp(parity, "MISMATCH") != 0) ? 0 : 1;
+           verify_ms, ok ? "true" : "false", parity, wm_parity);
+    return (ok && sat && strcmp(parity, "MISMATCH") != 0 && strcmp(wm_parity, "MISMATCH") != 0) ? 0 : 1;
 }

@@ -350,6 +350,21 @@ def fr_step_fft(a, log_big, log_small, mode=0, g=None):
     return a
 
 
+def qap_h_coefficients(aA, aB, aC, log_big, log_small, g, div):
+    """The vector part of libsnark's r1cs_to_qap_witness_map for d1 = d2 = d3 = 0 (r1cs_to_qap.tcc:232-311): evaluations of
+    A, B, C on the domain -> coefficients of H = (A B - C) / Z.  log_small = None: basic radix-2 domain of 2^log_big points
+    (div = [Z^-1]); else the step domain of 2^log_big + 2^log_small points (div = [c1, ratio, c0, Z1^-1])."""
+    aA, aB, aC = _arr(aA, 4), _arr(aB, 4), _arr(aC, 4)
+    m = (1 << log_big) + (0 if log_small is None else 1 << log_small)
+    if not (aA.shape[0] == aB.shape[0] == aC.shape[0] == m):
+        raise ValueError("expected m values per vector")
+    g, div = _arr(g, 4), _arr(div, 4)
+    H = np.zeros((m, 4), dtype=np.uint64)
+    ls = ctypes.c_size_t(2 ** 64 - 1) if log_small is None else _sz(log_small)
+    _check(lib().b200_qap_h_coefficients(_p(aA), _p(aB), _p(aC), _sz(log_big), ls, _p(g), _p(div), _p(H)), "b200_qap_h_coefficients")
+    return H
+
+
 def scale_inv_geometric(P, n_geo, c1, ratio, c0, tail=None):
     """P[i] *= (c1 * ratio^i - c0)^-1 for i < n_geo and P[n_geo + i] *= tail: the divisions of libfqfft's
     step_radix2_domain::divide_by_Z_on_coset (step_radix2_domain.tcc:213-241) with caller-formed constants."""

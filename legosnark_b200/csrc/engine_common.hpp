@@ -253,6 +253,8 @@ const void *fr_fold_device(Device &D, const uint64_t *v, const uint64_t *r, size
 int fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t *eval);
 int fr_mle_bind(const uint64_t *table, size_t half, const uint64_t *r, uint64_t *out);
 int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, void *stream);
+int fr_qap_h(const uint64_t *aA, const uint64_t *aB, const uint64_t *aC, size_t log_big, size_t log_small, const uint64_t *g,
+             const uint64_t *div, uint64_t *H);
 int fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *g);
 int fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t *c1, const uint64_t *ratio, const uint64_t *c0, size_t n_tail,
                            const uint64_t *tail);

@@ -436,6 +436,12 @@ int b200_cppoly_prove_g1(uint64_t key, const uint64_t *v, const uint64_t *r, siz
     std::lock_guard<std::mutex> lk(g_mu);
     return cppoly_prove_g1(key, v, r, d, witness, eval);
 }
+int b200_qap_h_coefficients(const uint64_t *aA, const uint64_t *aB, const uint64_t *aC, size_t log_big, size_t log_small,
+                            const uint64_t coset_g[4], const uint64_t *div_consts, uint64_t *H)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return fr_qap_h(aA, aB, aC, log_big, log_small, coset_g, div_consts, H);
+}
 int b200_fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *coset_g)
 {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -472,11 +472,61 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
 // (step_radix2_domain.tcc:38-152).  The two radix-2 transforms inside are fr_fft on device buffers; the loops around
 // them are the k_step_* kernels.  One upload, one download.
 // ------------------------------------------------------------------------------
-static DevBuf g_st_a, g_st_c, g_st_d, g_st_e, g_st_part, g_st_gp, g_st_const;
+static DevBuf g_st_a, g_st_c, g_st_d, g_st_e, g_st_part, g_st_gp, g_st_const, g_st_half;
+void fr_qap_release();
 void fr_step_release()
 {
-    DevBuf *all[] = {&g_st_a, &g_st_c, &g_st_d, &g_st_e, &g_st_part, &g_st_gp, &g_st_const};
+    DevBuf *all[] = {&g_st_a, &g_st_c, &g_st_d, &g_st_e, &g_st_part, &g_st_gp, &g_st_const, &g_st_half};
     for (DevBuf *b : all) b->release();
+    fr_qap_release();
+}
+
+// 1/2 in Fr, Montgomery form ((r + 1) / 2 * 2^256 mod r): FieldT(2).inverse() of step_radix2_domain.tcc:127
+static const uint32_t FR_HALF[8] = {0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu, 0xfcfd4f45u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au};
+
+// table[i] = g^i (inverse == false) or g^-i, i < m, from the host element g; cst: 8 Fr of device scratch
+static void coset_table_device(Device &D, cudaStream_t st, const uint64_t *g, bool inverse, size_t m, Fr *cst, Fr *table)
+{
+    CK(cudaMemcpyAsync(cst + 6, g, sizeof(Fr), cudaMemcpyHostToDevice, st));
+    LAUNCH(D, k_fr_domain_consts, 1, 32, 0, st, 1u, (const Fr *)(cst + 6), cst);  // cst[3] = g, cst[4] = g^-1
+    LAUNCH(D, k_fr_pow_table, cdiv(cdiv(m, 16), 128), 128, 0, st, (const Fr *)(cst + (inverse ? 4 : 3)), (const Fr *)nullptr, m, table);
+}
+
+// One step_radix2_domain transform of the m = 2^log_big + 2^log_small values at A (device, in place) on `st`:
+// inverse == false: FFT (gp != nullptr: cosetFFT, gp[i] = g^i); inverse == true: iFFT (gp != nullptr: icosetFFT, gp[i] = g^-i).
+static int step_transform_device(Device &D, cudaStream_t st, Fr *A, size_t log_big, size_t log_small, bool inverse, const Fr *gp)
+{
+    const size_t big = (size_t)1 << log_big, small = (size_t)1 << log_small, compr = big / small;
+    g_st_c.ensure(big * sizeof(Fr));
+    g_st_d.ensure(big * sizeof(Fr));
+    g_st_e.ensure(small * sizeof(Fr));
+    g_st_half.ensure(sizeof(Fr));
+    const uint32_t J = (uint32_t)std::max<size_t>(1, std::min<size_t>(compr, std::max<size_t>(1, ((size_t)1 << 16) / small)));
+    g_st_part.ensure((size_t)J * small * sizeof(Fr));
+    // omega^i / omega^-i, i < big: the twiddle tables of the radix-2 domain of size 2 * big (omega = its root of unity, :31)
+    FrDomain &dm2 = domain_for(D, 0, (uint32_t)log_big + 1, nullptr, st);
+    const Fr *ow = dm2.tw_fwd.as<Fr>(), *owi = dm2.tw_inv.as<Fr>();
+    Fr *C = g_st_c.as<Fr>(), *Dd = g_st_d.as<Fr>(), *E = g_st_e.as<Fr>(), *part = g_st_part.as<Fr>();
+    if (!inverse) {
+        LAUNCH(D, k_step_fwd_pre, cdiv(big, 256), 256, 0, st, (const Fr *)A, gp, ow, big, small, C, Dd);
+        LAUNCH(D, k_step_strided_partial, cdiv(small * J, 256), 256, 0, st, (const Fr *)Dd, (const Fr *)nullptr, small, compr, 0u, J, part);
+        LAUNCH(D, k_step_strided_final, cdiv(small, 256), 256, 0, st, (const Fr *)part, small, J, E);
+        int rc = fr_fft(nullptr, C, log_big, 0, nullptr, st);
+        if (rc == B200_OK && log_small >= 1) rc = fr_fft(nullptr, E, log_small, 0, nullptr, st);
+        if (rc != B200_OK) return rc;
+        CK(cudaMemcpyAsync(A, C, big * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(A + big, E, small * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    } else {
+        int rc = fr_fft(nullptr, A, log_big, 1, nullptr, st);
+        if (rc == B200_OK && log_small >= 1) rc = fr_fft(nullptr, A + big, log_small, 1, nullptr, st);
+        if (rc != B200_OK) return rc;
+        CK(cudaMemcpyAsync(g_st_half.p, FR_HALF, sizeof(Fr), cudaMemcpyHostToDevice, st));
+        LAUNCH(D, k_step_strided_partial, cdiv(small * J, 256), 256, 0, st, (const Fr *)A, ow, small, compr, 1u, J, part);
+        LAUNCH(D, k_step_strided_final, cdiv(small, 256), 256, 0, st, (const Fr *)part, small, J, E);
+        LAUNCH(D, k_step_inv_post, cdiv(big, 256), 256, 0, st, (const Fr *)A, (const Fr *)(A + big), (const Fr *)E, owi, gp,
+               (const Fr *)g_st_half.as<Fr>(), big, small, A);
+    }
+    return B200_OK;
 }
 
 int fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *g)
@@ -485,71 +535,112 @@ int fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const u
     if (!a || mode < 0 || mode > 3) return fail(B200_ERR_ARG, "bad argument");
     if (log_small >= log_big || log_big + 1 > FR_TWO_ADICITY) return fail(B200_ERR_ARG, "step_radix2: expected small_m < big_m and 2 big_m | 2^28");
     if (mode >= 2 && !g) return fail(B200_ERR_ARG, "coset transforms need the shift g");
-    // 1/2 in Fr, Montgomery form ((r + 1) / 2 * 2^256 mod r): FieldT(2).inverse() of step_radix2_domain.tcc:127
-    static const uint32_t HALF[8] = {0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu, 0xfcfd4f45u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au};
     try {
         Device &D = g_devs[0];
         CK(cudaSetDevice(D.id));
         cudaStream_t st = D.stream;
-        const size_t big = (size_t)1 << log_big, small = (size_t)1 << log_small, m = big + small, compr = big / small;
+        const size_t m = ((size_t)1 << log_big) + ((size_t)1 << log_small);
         const bool inverse = mode == 1 || mode == 3, coset = mode >= 2;
-        uint32_t launches = 0;
-        D.launches = 0;
         g_st_a.ensure(m * sizeof(Fr));
-        g_st_c.ensure(big * sizeof(Fr));
-        g_st_d.ensure(big * sizeof(Fr));
-        g_st_e.ensure(small * sizeof(Fr));
         g_st_const.ensure(8 * sizeof(Fr));
-        const uint32_t J = (uint32_t)std::max<size_t>(1, std::min<size_t>(compr, std::max<size_t>(1, ((size_t)1 << 16) / small)));
-        g_st_part.ensure((size_t)J * small * sizeof(Fr));
         h2d(D, g_st_a.p, a, m * sizeof(Fr), st);
-        // omega^i / omega^-i, i < big: the twiddle tables of the radix-2 domain of size 2 * big (omega = its root of unity, :31)
-        FrDomain &dm2 = domain_for(D, 0, (uint32_t)log_big + 1, nullptr, st);
-        const Fr *ow = dm2.tw_fwd.as<Fr>(), *owi = dm2.tw_inv.as<Fr>();
         const Fr *gp = nullptr;
-        Fr *cst = g_st_const.as<Fr>();
-        CK(cudaMemcpyAsync(cst + 5, HALF, sizeof(Fr), cudaMemcpyHostToDevice, st));
         if (coset) {  // g^i (cosetFFT) or g^-i (icosetFFT), i < m
             g_st_gp.ensure(m * sizeof(Fr));
-            CK(cudaMemcpyAsync(cst + 6, g, sizeof(Fr), cudaMemcpyHostToDevice, st));
-            LAUNCH(D, k_fr_domain_consts, 1, 32, 0, st, 1u, (const Fr *)(cst + 6), cst);  // cst[3] = g, cst[4] = g^-1
-            LAUNCH(D, k_fr_pow_table, cdiv(cdiv(m, 16), 128), 128, 0, st, (const Fr *)(cst + (inverse ? 4 : 3)), (const Fr *)nullptr, m,
-                   g_st_gp.as<Fr>());
+            coset_table_device(D, st, g, inverse, m, g_st_const.as<Fr>(), g_st_gp.as<Fr>());
             gp = g_st_gp.as<Fr>();
         }
-        Fr *A = g_st_a.as<Fr>(), *C = g_st_c.as<Fr>(), *Dd = g_st_d.as<Fr>(), *E = g_st_e.as<Fr>(), *part = g_st_part.as<Fr>();
-        launches += D.launches;
-        if (!inverse) {
-            LAUNCH(D, k_step_fwd_pre, cdiv(big, 256), 256, 0, st, (const Fr *)A, gp, ow, big, small, C, Dd);
-            LAUNCH(D, k_step_strided_partial, cdiv(small * J, 256), 256, 0, st, (const Fr *)Dd, (const Fr *)nullptr, small, compr, 0u, J, part);
-            LAUNCH(D, k_step_strided_final, cdiv(small, 256), 256, 0, st, (const Fr *)part, small, J, E);
-            launches += D.launches;
-            int rc = fr_fft(nullptr, C, log_big, 0, nullptr, st);
-            launches += D.launches;
-            if (rc == B200_OK && log_small >= 1) rc = fr_fft(nullptr, E, log_small, 0, nullptr, st);
-            if (rc != B200_OK) return rc;
-            launches += D.launches;
-            d2h(D, a, C, big * sizeof(Fr), st);
-            d2h(D, a + 4 * big, E, small * sizeof(Fr), st);
-        } else {
-            int rc = fr_fft(nullptr, A, log_big, 1, nullptr, st);
-            launches += D.launches;
-            if (rc == B200_OK && log_small >= 1) rc = fr_fft(nullptr, A + big, log_small, 1, nullptr, st);
-            if (rc != B200_OK) return rc;
-            launches += D.launches;
-            D.launches = 0;
-            LAUNCH(D, k_step_strided_partial, cdiv(small * J, 256), 256, 0, st, (const Fr *)A, ow, small, compr, 1u, J, part);
-            LAUNCH(D, k_step_strided_final, cdiv(small, 256), 256, 0, st, (const Fr *)part, small, J, E);
-            LAUNCH(D, k_step_inv_post, cdiv(big, 256), 256, 0, st, (const Fr *)A, (const Fr *)(A + big), (const Fr *)E, owi, gp, (const Fr *)(cst + 5),
-                   big, small, A);
-            launches += D.launches;
-            d2h(D, a, A, m * sizeof(Fr), st);
-        }
+        const int rc = step_transform_device(D, st, g_st_a.as<Fr>(), log_big, log_small, inverse, gp);
+        if (rc != B200_OK) return rc;
+        d2h(D, a, g_st_a.p, m * sizeof(Fr), st);
         CK(cudaStreamSynchronize(st));
         g_stats = b200_stats_t{};
         g_stats.n = m;
-        g_stats.kernel_launches = launches;
         g_stats.h2d_bytes = g_stats.d2h_bytes = (double)m * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
+    }
+}
+
+// ------------------------------------------------------------------------------
+// The vector part of r1cs_to_qap_witness_map (SNK/reductions/r1cs_to_qap/r1cs_to_qap.tcc:232-311) for d1 = d2 = d3 = 0
+// (what every Groth16 / LegoGroth prover passes): from the evaluations aA, aB, aC of the constraint polynomials on the
+// domain S to the coefficients of H = (A B - C) / Z,
+//     A, B, C <- iFFT;  A, B, C <- cosetFFT(g);  T = A B - C;  T <- T / Z on the coset;  H <- icosetFFT(T, g).
+// Seven transforms with nothing leaving the device in between (the reference runs them one by one on host vectors; through
+// the per-transform shims each of them was an upload and a download).  log_small == QAP_BASIC: basic radix-2 domain of
+// 2^log_big points, div = {Z^-1}; otherwise the step domain of 2^log_big + 2^log_small points, div = {c1, ratio, c0, Z1^-1}
+// (the constants of step_radix2_domain::divide_by_Z_on_coset, formed by the caller).
+// ------------------------------------------------------------------------------
+static DevBuf g_q[3], g_q_gp, g_q_gip;
+void fr_qap_release()
+{
+    for (auto &b : g_q) b.release();
+    g_q_gp.release();
+    g_q_gip.release();
+}
+
+int fr_qap_h(const uint64_t *aA, const uint64_t *aB, const uint64_t *aC, size_t log_big, size_t log_small, const uint64_t *g,
+             const uint64_t *div, uint64_t *H)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!aA || !aB || !aC || !g || !div || !H) return fail(B200_ERR_ARG, "null argument");
+    const bool basic = log_small == (size_t)-1;
+    if (log_big < 1 || log_big + (basic ? 0 : 1) > FR_TWO_ADICITY || (!basic && log_small >= log_big)) return fail(B200_ERR_ARG, "bad domain");
+    try {
+        Device &D = g_devs[0];
+        CK(cudaSetDevice(D.id));
+        D.launches = 0;
+        cudaStream_t st = D.stream;
+        const size_t big = (size_t)1 << log_big, small = basic ? 0 : (size_t)1 << log_small, m = big + small;
+        const uint64_t *src[3] = {aA, aB, aC};
+        for (int k = 0; k < 3; k++) {
+            g_q[k].ensure(m * sizeof(Fr));
+            h2d(D, g_q[k].p, src[k], m * sizeof(Fr), st);
+        }
+        g_st_const.ensure(16 * sizeof(Fr));
+        Fr *cst = g_st_const.as<Fr>();
+        Fr *X = g_q[0].as<Fr>(), *Y = g_q[1].as<Fr>(), *Z = g_q[2].as<Fr>();
+        if (basic) {
+            for (Fr *v : {X, Y, Z}) {
+                int rc = fr_fft(nullptr, v, log_big, 1, nullptr, st);
+                if (rc == B200_OK) rc = fr_fft(nullptr, v, log_big, 2, g, st);
+                if (rc != B200_OK) return rc;
+            }
+        } else {
+            g_q_gp.ensure(m * sizeof(Fr));
+            g_q_gip.ensure(m * sizeof(Fr));
+            coset_table_device(D, st, g, false, m, cst, g_q_gp.as<Fr>());
+            coset_table_device(D, st, g, true, m, cst, g_q_gip.as<Fr>());
+            for (Fr *v : {X, Y, Z}) {
+                int rc = step_transform_device(D, st, v, log_big, log_small, true, nullptr);
+                if (rc == B200_OK) rc = step_transform_device(D, st, v, log_big, log_small, false, g_q_gp.as<Fr>());
+                if (rc != B200_OK) return rc;
+            }
+        }
+        LAUNCH(D, k_fr_mul_sub, cdiv(m, 256), 256, 0, st, X, (const Fr *)Y, (const Fr *)Z, m);
+        CK(cudaMemcpyAsync(cst + 8, div, (basic ? 1 : 4) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        if (basic) {
+            LAUNCH(D, k_fr_scale, cdiv(m, 256), 256, 0, st, X, m, (const Fr *)(cst + 8));
+            const int rc = fr_fft(nullptr, X, log_big, 3, g, st);
+            if (rc != B200_OK) return rc;
+        } else {
+            LAUNCH(D, k_fr_scale_inv_geometric, cdiv(cdiv(big, INVG_RUN), 128), 128, 0, st, X, big, (const Fr *)(cst + 8));
+            LAUNCH(D, k_fr_scale, cdiv(small, 256), 256, 0, st, X + big, small, (const Fr *)(cst + 11));
+            const int rc = step_transform_device(D, st, X, log_big, log_small, true, g_q_gip.as<Fr>());
+            if (rc != B200_OK) return rc;
+        }
+        d2h(D, H, X, m * sizeof(Fr), st);
+        CK(cudaStreamSynchronize(st));
+        g_stats = b200_stats_t{};
+        g_stats.n = m;
+        g_stats.h2d_bytes = 3.0 * m * sizeof(Fr);
+        g_stats.d2h_bytes = (double)m * sizeof(Fr);
         return B200_OK;
     } catch (const CudaError &e) {
         return fail(B200_ERR_CUDA, "%s", e.msg.c_str());

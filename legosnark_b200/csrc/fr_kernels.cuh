@@ -284,6 +284,13 @@ static __global__ void __launch_bounds__(128) k_fr_scale_inv_geometric(Fr *__res
     }
 }
 
+// x[i] = x[i] * y[i] - z[i], i < n: H on the coset before the division, r1cs_to_qap.tcc:270-300
+static __global__ void __launch_bounds__(256) k_fr_mul_sub(Fr *__restrict__ x, const Fr *__restrict__ y, const Fr *__restrict__ z, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = Fr::sub(Fr::mul(x[i], y[i]), z[i]);
+}
+
 // P[i] *= s, i < n
 static __global__ void __launch_bounds__(256) k_fr_scale(Fr *__restrict__ P, size_t n, const Fr *__restrict__ s)
 {

@@ -118,6 +118,33 @@ def test_gpu_step_domain_vs_oracle(engine, orc, lb, ls):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lb,ls", [(3, 0), (6, 2), (10, 0), (12, 11), (13, None), (5, None)])
+def test_gpu_qap_h_coefficients(engine, orc, lb, ls):
+    """b200_qap_h_coefficients = the vector part of r1cs_to_qap_witness_map (r1cs_to_qap.tcc:232-311, d1 = d2 = d3 = 0):
+    iFFT x 3, cosetFFT x 3, A B - C, divide_by_Z_on_coset, icosetFFT, composed here from the pinned restatements
+    (orc_fr_step_fft / orc_fr_fft, the reference-checked division formula) on step domains (2^r = 1 and > 1) and basic ones."""
+    r = R_ORDER
+    m = (1 << lb) + (0 if ls is None else 1 << ls)
+    a, b, c = (orc.sha512_rng_fr(4400 + 10 * lb + k, m) for k in range(3))
+    g5 = ints_to_mont([5], r)
+
+    def fwd(v, mode):
+        return orc.fr_fft(v, mode, g5) if ls is None else orc.fr_step_fft(v, lb, ls, mode, g5)
+    A, B, C = (fwd(fwd(v, 1), 2) for v in (a, b, c))
+    T = orc.field_op("fr", 3, orc.field_op("fr", 0, A, B), C)  # A * B - C
+    if ls is None:
+        zinv = pow((pow(5, m, r) - 1) % r, -1, r)
+        T = ints_to_mont([x * zinv % r for x in mont_to_ints(T, r)], r)
+        div = ints_to_mont([zinv], r)
+    else:
+        T, (c1, ratio, c0, z1i) = _step_divide_z_expected(T, lb, ls)
+        div = ints_to_mont([c1, ratio, c0, z1i], r)
+    want = fwd(T, 3)
+    got = engine.qap_h_coefficients(a, b, c, lb, ls, g5, div)
+    assert (got == want).all()
+
+
+@pytest.mark.gpu
 def test_gpu_step_domain_round_trip_at_scale(engine):
     """2^21 + 1 points (the 128 x 128 matrix product): iFFT(FFT(a)) = a and icosetFFT(cosetFFT(a)) = a."""
     lb, ls = 21, 0
