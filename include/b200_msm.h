@@ -207,6 +207,18 @@ int b200_qap_h_coefficients(const uint64_t *aA /* m x 4 */, const uint64_t *aB /
 int b200_fr_scale_inv_geometric(uint64_t *P /* (n_geo + n_tail) x 4 */, size_t n_geo, const uint64_t c1[4], const uint64_t ratio[4],
                                 const uint64_t c0[4], size_t n_tail, const uint64_t *tail /* 4 */);
 
+/* The Lagrange-coefficient vectors of libfqfft's radix-2 and step domains: _basic_radix2_evaluate_all_lagrange_polynomials
+ * (FQFFT/evaluation_domain/domains/basic_radix2_domain_aux.tcc:183-236: u[i] = l * (t - r).inverse(); l *= omega; r *= omega) and
+ * step_radix2_domain::evaluate_all_lagrange_polynomials (step_radix2_domain.tcc:161-186), which libsnark's generators call through
+ * r1cs_to_qap_instance_map_with_evaluation (SNK/reductions/r1cs_to_qap/r1cs_to_qap.tcc:127-190).  Both spend ONE FIELD INVERSION
+ * PER POINT on the host (5.4 of the 5.7 host seconds of the Groth16 generator for the 128 x 128 matrix product of BASELINE.json
+ * configs[3]).  out[i] = in[i] * a0 * a_ratio^i / prod_f (c1_f * ratio_f^i - c0_f) for i < n and f < n_factors (1 or 2);
+ * in == NULL means in[i] = 1, in == out is allowed.  consts = a0, a_ratio, then (c1, ratio, c0) per factor: (2 + 3 n_factors) x 4
+ * limbs, formed by the caller (shim/libfqfft/.../basic_radix2_domain_aux.hpp, step_radix2_domain.hpp).  No denominator may be
+ * zero (the reference tests t^m == 1 first and so do the shadows).  Batched inversion on the device; same limbs. */
+int b200_fr_geometric_quotients(uint64_t *out /* n x 4 */, const uint64_t *in /* n x 4 or NULL */, size_t n, const uint64_t *consts,
+                                size_t n_factors);
+
 /* Sum-check dynamic-programming tables (LS/prototools/mle.h, LS/gadgets/sumcheck.h; all values Montgomery-form Fr).
  * b200_fr_eq_table: DPBeta::compute_eq_tbl (mle.h:93-105), level by level exactly as written there:
  *   T_0 = {1};  T_{j+1}[p] = eqbit(p >= 2^j, r[j]) * T_j[p >> 1], p < 2^(j+1);  out = T_d.

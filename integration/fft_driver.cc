@@ -54,9 +54,20 @@ static void run(size_t m, const char *impl)
     t0 = now_ms();
     dom->FFT(a);
     const double fft2_ms = now_ms() - t0;
+    // the generators' side of the domain (r1cs_to_qap_instance_map_with_evaluation, r1cs_to_qap.tcc:127-190): all Lagrange
+    // coefficients at a random point, and at a point of the domain itself (the reference's unit-vector branch)
+    harness::Fingerprint fl;
+    const FrT tpt = harness::scalars<FrT>(1, 11)[0];
+    t0 = now_ms();
+    const vector<FrT> lag = dom->evaluate_all_lagrange_polynomials(tpt);
+    const double lagrange_ms = now_ms() - t0;
+    fp_vec(fl, lag);
+    fp_vec(fl, dom->evaluate_all_lagrange_polynomials(dom->get_domain_element(dom->m / 3)));
     printf("{\"example\": \"fft\", \"impl\": \"%s\", \"m\": %zu, \"domain_m\": %zu, \"fft_ms_first\": %.3f, \"fft_ms\": %.3f, "
-           "\"ifft_ms\": %.3f, \"coset_fft_divide_icoset_ms\": %.3f, \"round_trip\": %s, \"fingerprint\": \"%s\"}\n",
-           impl, m, (size_t)dom->m, fft_ms, fft2_ms, ifft_ms, coset_ms, round_trip ? "true" : "false", fp.hex().c_str());
+           "\"ifft_ms\": %.3f, \"coset_fft_divide_icoset_ms\": %.3f, \"round_trip\": %s, \"fingerprint\": \"%s\", "
+           "\"lagrange_ms\": %.3f, \"lagrange_fingerprint\": \"%s\"}\n",
+           impl, m, (size_t)dom->m, fft_ms, fft2_ms, ifft_ms, coset_ms, round_trip ? "true" : "false", fp.hex().c_str(), lagrange_ms,
+           fl.hex().c_str());
 }
 
 int main(int argc, char **argv)

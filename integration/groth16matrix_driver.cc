@@ -49,7 +49,7 @@ int main(int argc, char **argv)
     const int n = argc > 1 ? atoi(argv[1]) : 16;
     const int parity_max_n = argc > 2 ? atoi(argv[2]) : 128;
     libff::inhibit_profiling_info = getenv("B200_DRIVER_PROFILE") == nullptr;  // libff's enter/leave_block timings
-    libff::inhibit_profiling_counters = true;
+    libff::inhibit_profiling_counters = libff::inhibit_profiling_info;  // the counters also gate enter/leave_block (profiling.cpp:247)
     ppT::init_public_params();
     srand(1);
 

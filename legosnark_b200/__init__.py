@@ -379,6 +379,84 @@ def scale_inv_geometric(P, n_geo, c1, ratio, c0, tail=None):
     return P
 
 
+def geometric_quotients(n, consts, inp=None):
+    """out[i] = inp[i] * a0 * a_ratio^i / prod_f (c1_f * ratio_f^i - c0_f), i < n (b200_fr_geometric_quotients); consts = rows
+    a0, a_ratio, then (c1, ratio, c0) per factor (one or two factors), Montgomery-form Fr."""
+    consts = _arr(consts, 4)
+    nf, rem = divmod(consts.shape[0] - 2, 3)
+    if rem or nf not in (1, 2):
+        raise ValueError("consts must hold 2 + 3 * n_factors rows")
+    out = np.zeros((n, 4), dtype=np.uint64)
+    if inp is not None:
+        inp = _arr(inp, 4)
+        if inp.shape[0] != n:
+            raise ValueError("inp must hold n values")
+    _check(lib().b200_fr_geometric_quotients(_p(out), None if inp is None else _p(inp), _sz(n), _p(consts), _sz(nf)),
+           "b200_fr_geometric_quotients")
+    return out
+
+
+_FR_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617  # alt_bn128_init.cpp:40
+_FR_ROOT_2_28 = 19103219067921713944291392827692070036145651957329286315305642004821462161904  # Fr::root_of_unity, alt_bn128_init.cpp:60
+
+
+def _fr_rows(values):
+    """Python integers -> Montgomery-form limb rows (R = 2^256, fp.hpp:42)."""
+    out = np.zeros((len(values), 4), dtype=np.uint64)
+    for i, v in enumerate(values):
+        m = (v % _FR_MOD) * (1 << 256) % _FR_MOD
+        for k in range(4):
+            out[i, k] = (m >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def _fr_int(row):
+    m = sum(int(row[k]) << (64 * k) for k in range(4))
+    return m * pow(1 << 256, -1, _FR_MOD) % _FR_MOD
+
+
+def evaluate_all_lagrange_polynomials(log_big, log_small, t):
+    """evaluate_all_lagrange_polynomials(t) of libfqfft's basic_radix2_domain (log_small None; basic_radix2_domain_aux.tcc:183-236)
+    or step_radix2_domain (2^log_big + 2^log_small points; step_radix2_domain.tcc:161-186).  The host forms the constants the way
+    the shadow headers do (shim/libfqfft/.../basic_radix2_domain_aux.hpp, step_radix2_domain.hpp); the per-point divisions run on
+    the device.  t on the domain itself gives the reference's unit vector (aux.tcc:201-214)."""
+    r = _FR_MOD
+    tv = _fr_int(_arr(t, 4).reshape(-1, 4)[0])
+
+    def basic(log_m, tt, scale, extra=None):
+        m = 1 << log_m
+        if m == 1:
+            return _fr_rows([scale])
+        omega = pow(_FR_ROOT_2_28, 1 << (28 - log_m), r)
+        tm = pow(tt, m, r)
+        if tm == 1:  # t is omega^k: 1 at k, 0 elsewhere (times what the step domain multiplies in)
+            out = np.zeros((m, 4), dtype=np.uint64)
+            k = next(i for i in range(m) if pow(omega, i, r) == tt)
+            f = scale
+            if extra is not None:
+                c1, ratio, c0 = extra
+                f = f * pow((c1 * pow(ratio, k, r) - c0) % r, -1, r) % r
+            out[k] = _fr_rows([f])[0]
+            return out
+        l0 = (tm - 1) * pow(m, -1, r) % r * scale % r
+        rows = [l0, omega, r - 1, omega, (r - tt) % r]  # l0 omega^i / (t - omega^i)
+        if extra is not None:
+            rows += list(extra)
+        return geometric_quotients(m, _fr_rows(rows))
+
+    if log_small is None:
+        return basic(log_big, tv, 1)
+    big, small = 1 << log_big, 1 << log_small
+    omega = pow(_FR_ROOT_2_28, 1 << (28 - (log_big + 1)), r)
+    big_omega = omega * omega % r
+    w = pow(omega, small, r)
+    L0 = (pow(tv, small, r) - w) % r
+    L1 = (pow(tv, big, r) - 1) * pow((pow(omega, big, r) - 1) % r, -1, r) % r
+    head = basic(log_big, tv, L0, (1, pow(big_omega, small, r), w))  # inner_big[i] * L0 / (rho^i - omega^small)
+    tail = basic(log_small, tv * pow(omega, -1, r) % r, L1)
+    return np.concatenate([head, tail])
+
+
 def compute_eq_tbl(r):
     """DPBeta::compute_eq_tbl (LS/prototools/mle.h:93-105): the 2^d-entry table, level by level as the reference writes it."""
     r = _arr(r, 4)

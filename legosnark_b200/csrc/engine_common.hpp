@@ -256,6 +256,7 @@ int fr_fft(uint64_t *a, void *d_a, size_t log_n, int mode, const uint64_t *g, vo
 int fr_qap_h(const uint64_t *aA, const uint64_t *aB, const uint64_t *aC, size_t log_big, size_t log_small, const uint64_t *g,
              const uint64_t *div, uint64_t *H);
 int fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *g);
+int fr_geometric_quotients(uint64_t *out, const uint64_t *in, size_t n, const uint64_t *consts, size_t nf);
 int fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t *c1, const uint64_t *ratio, const uint64_t *c0, size_t n_tail,
                            const uint64_t *tail);
 int fr_eq_table(const uint64_t *r, size_t d, uint64_t *out);

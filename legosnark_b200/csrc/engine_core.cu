@@ -1,5 +1,7 @@
 // engine_core.cu — lifecycle, shared state and the extern "C" surface declared in
 // include/b200_msm.h.  The per-group work is in engine_g1.cu / engine_g2.cu.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 
 #include "engine_common.hpp"
@@ -13,6 +15,12 @@ namespace eng {
 
 std::mutex g_mu;
 std::string g_err;
+// B200_TRACE=1: one stderr line per C-ABI call (ApiScope below) and per phase of b200_init
+static const bool g_trace = [] { const char *e = std::getenv("B200_TRACE"); return e && *e && *e != '0'; }();
+static double trace_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 int fail(int code, const char *fmt, ...)
 {
@@ -87,7 +95,15 @@ int init_devices(const int *ids, int n)
 {
     if (g_init) return B200_OK;
     int visible = 0;
+    double tr0 = g_trace ? trace_ms() : 0;
+    auto phase = [&](const char *what) {
+        if (!g_trace) return;
+        const double now = trace_ms();
+        fprintf(stderr, "[b200]   init: %-40s %9.3f ms\n", what, now - tr0);
+        tr0 = now;
+    };
     cudaError_t e = cudaGetDeviceCount(&visible);
+    phase("cudaGetDeviceCount (driver start-up)");
     if (e != cudaSuccess || visible == 0)
         return fail(B200_ERR_NO_DEVICE, "no CUDA device visible (%s); this engine has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
@@ -111,6 +127,7 @@ int init_devices(const int *ids, int n)
             CK(cudaGetDeviceProperties(&prop, D.id));
             D.sms = prop.multiProcessorCount;
             CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+            phase("context + first stream");
             CK(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
             for (auto &e : D.ev) CK(cudaEventCreate(&e));
             for (auto &e : D.ev_ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -123,8 +140,10 @@ int init_devices(const int *ids, int n)
             D.window_sums.ensure((size_t)64 * 256);
             D.totals.ensure(32);
             D.ensure_pinned((size_t)64 * 256 + 1024);
+            phase("streams, events, small-path buffers");
             preload_small_path<Fq>();
             preload_small_path<Fq2>();
+            phase("small-path kernels loaded");
         }
     } catch (const CudaError &e2) {
         g_devs.clear();
@@ -198,18 +217,39 @@ static int apply_env_tuning()
     return B200_OK;
 }
 
+// One object per C-ABI call: holds the engine lock and, with B200_TRACE=1 in the environment, prints the call's wall time and
+// the size / transfer counters of the last pipeline to stderr when it returns (what a maintainer reaches for when a whole
+// prover is slower than the sum of its kernels: first-call allocations, staging, host tails).
+struct ApiScope {
+    std::lock_guard<std::mutex> lk;
+    const char *fn;
+    std::chrono::steady_clock::time_point t0;
+    explicit ApiScope(const char *f) : lk(g_mu), fn(f)
+    {
+        if (g_trace) t0 = std::chrono::steady_clock::now();
+    }
+    ~ApiScope()
+    {
+        if (!g_trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[b200] %-28s %9.3f ms  (last pipeline: n=%llu c=%u W=%u device %.3f ms, h2d %.1f MB, d2h %.3f MB)\n", fn, ms,
+                (unsigned long long)g_stats.n, g_stats.window_bits, g_stats.num_windows, g_stats.device_ms, g_stats.h2d_bytes / 1e6,
+                g_stats.d2h_bytes / 1e6);
+    }
+};
+
 extern "C" {
 
 int b200_init(int n_gpus)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     const int rc = init_devices(nullptr, n_gpus);
     return rc == B200_OK ? apply_env_tuning() : rc;
 }
 
 int b200_init_devices(const int *device_ids, int n)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!device_ids || n <= 0) return fail(B200_ERR_ARG, "device list is empty");
     const int rc = init_devices(device_ids, n);
     return rc == B200_OK ? apply_env_tuning() : rc;
@@ -217,7 +257,7 @@ int b200_init_devices(const int *device_ids, int n)
 
 void b200_shutdown(void)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!g_init) return;
     for (auto &kv : g_pinned)
         for (auto &s : kv.second->shards) {
@@ -246,19 +286,19 @@ const char *b200_version(void) { return "b200-msm 0.1 (sm_100a)"; }
 
 int b200_msm_g1(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t out[12])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return msm_host<Fq>(bases, scalars, n, out);
 }
 int b200_msm_g2(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t out[24])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return msm_host<Fq2>(bases, scalars, n, out);
 }
 
 int b200_msm_g2g1(const uint64_t *g2_bases, const uint64_t *g1_bases, const uint64_t *scalars, size_t n, uint64_t out_g2[24],
                   uint64_t out_g1[12])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!out_g2 || !out_g1 || (n && (!g2_bases || !g1_bases || !scalars))) return fail(B200_ERR_ARG, "null argument");
     int rc = msm_host<Fq2>(g2_bases, scalars, n, out_g2);
     if (rc != B200_OK) return rc;
@@ -278,12 +318,12 @@ int b200_msm_g2g1(const uint64_t *g2_bases, const uint64_t *g1_bases, const uint
 
 int b200_msm_batch_g1(const uint64_t *bases, const uint64_t *scalars, const uint64_t *offsets, size_t count, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return msm_batch<Fq>(bases, scalars, offsets, count, out);
 }
 int b200_msm_batch_g2(const uint64_t *bases, const uint64_t *scalars, const uint64_t *offsets, size_t count, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return msm_batch<Fq2>(bases, scalars, offsets, count, out);
 }
 
@@ -292,27 +332,27 @@ int b200_sum_partials_g2(const uint64_t *pts, size_t n, uint64_t out[24]) { retu
 
 int b200_pin_bases_g1(const uint64_t *bases, size_t n, uint64_t *handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return pin_bases<Fq>(bases, nullptr, n, handle);
 }
 int b200_pin_bases_g2(const uint64_t *bases, size_t n, uint64_t *handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return pin_bases<Fq2>(bases, nullptr, n, handle);
 }
 int b200_pin_affine_dev_g1(const void *d_affine, size_t n, uint64_t *handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return pin_bases<Fq>(nullptr, d_affine, n, handle);
 }
 int b200_pin_affine_dev_g2(const void *d_affine, size_t n, uint64_t *handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return pin_bases<Fq2>(nullptr, d_affine, n, handle);
 }
 int b200_unpin_bases(uint64_t handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     auto it = g_pinned.find(handle);
     if (it == g_pinned.end()) return fail(B200_ERR_ARG, "unknown bases handle");
     for (auto &s : it->second->shards) {
@@ -326,33 +366,33 @@ int b200_unpin_bases(uint64_t handle)
 }
 int b200_key_precompute_g1(uint64_t handle, uint32_t window_bits)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return key_precompute<Fq>(handle, window_bits);
 }
 int b200_key_precompute_g2(uint64_t handle, uint32_t window_bits)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return key_precompute<Fq2>(handle, window_bits);
 }
 int b200_msm_pinned_g1(uint64_t handle, size_t offset, const uint64_t *scalars, size_t n, uint64_t out[12])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return msm_pinned<Fq>(handle, offset, scalars, nullptr, n, nullptr, out);
 }
 int b200_msm_pinned_g2(uint64_t handle, size_t offset, const uint64_t *scalars, size_t n, uint64_t out[24])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return msm_pinned<Fq2>(handle, offset, scalars, nullptr, n, nullptr, out);
 }
 int b200_msm_pinned_dev_g1(uint64_t handle, size_t offset, const void *d_scalars, size_t n, void *stream, uint64_t out[12])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
     return msm_pinned<Fq>(handle, offset, nullptr, d_scalars, n, stream, out);
 }
 int b200_msm_pinned_dev_g2(uint64_t handle, size_t offset, const void *d_scalars, size_t n, void *stream, uint64_t out[24])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
     return msm_pinned<Fq2>(handle, offset, nullptr, d_scalars, n, stream, out);
 }
@@ -362,27 +402,27 @@ size_t b200_exp_window_size_g2(size_t num_scalars) { return libff_window_size(G2
 
 int b200_batch_exp_g1(const uint64_t base[12], const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return batch_exp_once<Fq>(base, scalars, n, coeff, out);
 }
 int b200_batch_exp_g2(const uint64_t base[24], const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return batch_exp_once<Fq2>(base, scalars, n, coeff, out);
 }
 int b200_window_table_create_g1(const uint64_t base[12], size_t expected, uint64_t *handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return table_create<Fq>(base, expected, handle);
 }
 int b200_window_table_create_g2(const uint64_t base[24], size_t expected, uint64_t *handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return table_create<Fq2>(base, expected, handle);
 }
 int b200_window_table_destroy(uint64_t handle)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     auto it = g_tables.find(handle);
     if (it == g_tables.end()) return fail(B200_ERR_ARG, "unknown table handle");
     for (size_t di = 0; di < it->second->d_table.size(); di++) {
@@ -394,139 +434,144 @@ int b200_window_table_destroy(uint64_t handle)
 }
 int b200_batch_exp_table_g1(uint64_t handle, const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return batch_exp_table<Fq>(handle, scalars, nullptr, n, coeff, out, nullptr, nullptr);
 }
 int b200_batch_exp_table_g2(uint64_t handle, const uint64_t *scalars, size_t n, const uint64_t *coeff, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return batch_exp_table<Fq2>(handle, scalars, nullptr, n, coeff, out, nullptr, nullptr);
 }
 int b200_batch_exp_table_dev_g1(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *stream)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
     return batch_exp_table<Fq>(handle, nullptr, d_scalars, n, nullptr, nullptr, d_out, stream);
 }
 int b200_batch_exp_table_dev_g2(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *stream)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (n && !d_scalars) return fail(B200_ERR_ARG, "null device scalars");
     return batch_exp_table<Fq2>(handle, nullptr, d_scalars, n, nullptr, nullptr, d_out, stream);
 }
 
 int b200_fr_fold_witness(const uint64_t *v, const uint64_t *r, size_t d, uint64_t *w_coeffs, uint64_t eval[4])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_fold_witness(v, r, d, w_coeffs, eval);
 }
 int b200_fr_eval_mle(const uint64_t *v, const uint64_t *r, size_t d, uint64_t out[4])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!out) return fail(B200_ERR_ARG, "null argument");
     return fr_fold_witness(v, r, d, nullptr, out);
 }
 int b200_fr_mle_bind(const uint64_t *table, size_t half, const uint64_t r[4], uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_mle_bind(table, half, r, out);
 }
 int b200_cppoly_prove_g1(uint64_t key, const uint64_t *v, const uint64_t *r, size_t d, uint64_t *witness, uint64_t eval[4])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return cppoly_prove_g1(key, v, r, d, witness, eval);
 }
 int b200_qap_h_coefficients(const uint64_t *aA, const uint64_t *aB, const uint64_t *aC, size_t log_big, size_t log_small,
                             const uint64_t coset_g[4], const uint64_t *div_consts, uint64_t *H)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_qap_h(aA, aB, aC, log_big, log_small, coset_g, div_consts, H);
 }
 int b200_fr_step_fft(uint64_t *a, size_t log_big, size_t log_small, int mode, const uint64_t *coset_g)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_step_fft(a, log_big, log_small, mode, coset_g);
+}
+int b200_fr_geometric_quotients(uint64_t *out, const uint64_t *in, size_t n, const uint64_t *consts, size_t n_factors)
+{
+    ApiScope lk(__func__);
+    return fr_geometric_quotients(out, in, n, consts, n_factors);
 }
 int b200_fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t c1[4], const uint64_t ratio[4], const uint64_t c0[4], size_t n_tail,
                                 const uint64_t *tail)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_scale_inv_geometric(P, n_geo, c1, ratio, c0, n_tail, tail);
 }
 int b200_fr_eq_table(const uint64_t *r, size_t d, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_eq_table(r, d, out);
 }
 int b200_fr_matrix_mle(const uint64_t *A, const uint64_t *rho, size_t d, uint64_t *v)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_matrix_mle(A, rho, d, v);
 }
 int b200_fr_sumcheck_round(const uint64_t *a, const uint64_t *b, const uint64_t *w, size_t half, uint64_t out[12])
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_sumcheck_round(a, b, w, half, out);
 }
 int b200_fr_sumcheck_rounds(const uint64_t *a, const uint64_t *b, const uint64_t *r, size_t d, uint64_t *h)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return fr_sumcheck_rounds(a, b, r, d, h);
 }
 int b200_fr_fft(uint64_t *a, size_t log_n, int mode, const uint64_t *coset_g)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!a) return fail(B200_ERR_ARG, "null argument");
     return fr_fft(a, nullptr, log_n, mode, coset_g, nullptr);
 }
 int b200_fr_fft_dev(void *d_a, size_t log_n, int mode, const uint64_t *coset_g, void *cuda_stream)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!d_a) return fail(B200_ERR_ARG, "null argument");
     return fr_fft(nullptr, d_a, log_n, mode, coset_g, cuda_stream);
 }
 
 int b200_compress_g1(const uint64_t *pts, size_t n, int flavour, uint64_t *x_out, uint8_t *flags)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return compress_g1(pts, n, flavour, x_out, flags);
 }
 int b200_compress_g2(const uint64_t *pts, size_t n, int flavour, uint64_t *x_out, uint8_t *flags)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return compress_g2(pts, n, flavour, x_out, flags);
 }
 int b200_decompress_g1(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out, uint8_t *bad)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return decompress_g1(x, flags, n, flavour, pts_out, bad);
 }
 int b200_decompress_g2(const uint64_t *x, const uint8_t *flags, size_t n, int flavour, uint64_t *pts_out, uint8_t *bad)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return decompress_g2(x, flags, n, flavour, pts_out, bad);
 }
 
 int b200_batch_to_affine_g1(uint64_t *pts, size_t n)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return batch_to_affine<Fq>(pts, n);
 }
 int b200_batch_to_affine_g2(uint64_t *pts, size_t n)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return batch_to_affine<Fq2>(pts, n);
 }
 
 int b200_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     return test_field_op(field, op, a, b, n, out);
 }
 
 int b200_test_group_op(int group, int op, const uint64_t *a, const uint64_t *b, size_t n, uint32_t k, uint64_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (group == 0) return test_group_op<Fq>(op, a, b, n, k, out);
     if (group == 1) return test_group_op<Fq2>(op, a, b, n, k, out);
     return fail(B200_ERR_ARG, "bad group");
@@ -541,7 +586,7 @@ int b200_last_stats(b200_stats_t *out)
 
 int b200_set_tuning(int window_bits, int chunk_len)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     g_tune_c = window_bits;
     g_tune_L = chunk_len;
     return B200_OK;
@@ -549,7 +594,7 @@ int b200_set_tuning(int window_bits, int chunk_len)
 
 int b200_set_tuning_ex(const char *key, int value)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!key) return fail(B200_ERR_ARG, "null key");
     return apply_tuning(key, value);
 }
@@ -557,14 +602,14 @@ int b200_set_tuning_ex(const char *key, int value)
 
 int b200_set_pipeline_chunks(int chunks)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     g_tune_chunks = chunks;
     return B200_OK;
 }
 
 int b200_imad_peak(int kind, int iters, double *ops_per_sec, double *elapsed_ms)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiScope lk(__func__);
     if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called");
     if (!ops_per_sec || iters <= 0) return fail(B200_ERR_ARG, "bad argument");
     try {

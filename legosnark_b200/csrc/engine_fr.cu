@@ -314,6 +314,43 @@ int fr_scale_inv_geometric(uint64_t *P, size_t n_geo, const uint64_t *c1, const 
     }
 }
 
+// out[i] = in[i] * a0 * a_ratio^i / prod_f (c1_f ratio_f^i - c0_f): the Lagrange-coefficient vectors of libfqfft's radix-2 and
+// step domains (basic_radix2_domain_aux.tcc:183-236, step_radix2_domain.tcc:161-186) with the constants formed by the caller.
+// consts = a0, a_ratio, then (c1, ratio, c0) per factor: (2 + 3 nf) x 4 limbs.  in may be NULL (ones) or equal to out.
+int fr_geometric_quotients(uint64_t *out, const uint64_t *in, size_t n, const uint64_t *consts, size_t nf)
+{
+    if (!g_init) return fail(B200_ERR_NOT_INIT, "b200_init has not been called (no CUDA device => no result: there is no CPU fallback)");
+    if (!out || !consts) return fail(B200_ERR_ARG, "null argument");
+    if (nf < 1 || nf > 2) return fail(B200_ERR_ARG, "one or two denominator factors, got %zu", nf);
+    if (n == 0) return B200_OK;
+    try {
+        Device &D = g_devs[0];
+        D.launches = 0;
+        CK(cudaSetDevice(D.id));
+        cudaStream_t st = D.stream;
+        D.fr_a.ensure(n * sizeof(Fr));
+        D.fr_r.ensure(8 * sizeof(Fr));
+        if (in) h2d(D, D.fr_a.p, in, n * sizeof(Fr), st);
+        CK(cudaMemcpyAsync(D.fr_r.p, consts, (2 + 3 * nf) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        LAUNCH(D, k_fr_geometric_quotients, cdiv(cdiv(n, INVG_RUN), 128), 128, 0, st, in ? (const Fr *)D.fr_a.as<Fr>() : (const Fr *)nullptr,
+               D.fr_a.as<Fr>(), n, (const Fr *)D.fr_r.as<Fr>(), (int)nf);
+        d2h(D, out, D.fr_a.p, n * sizeof(Fr), st);
+        CK(cudaStreamSynchronize(st));  // consts belongs to the caller
+        g_stats = b200_stats_t{};
+        g_stats.n = n;
+        g_stats.kernel_launches = D.launches;
+        g_stats.h2d_bytes = in ? (double)n * sizeof(Fr) : 0.0;
+        g_stats.d2h_bytes = (double)n * sizeof(Fr);
+        return B200_OK;
+    } catch (const CudaError &e) {
+        return fail(B200_ERR_CUDA, "%s", e.msg.c_str());
+    } catch (const std::exception &ex) {  // nothing may unwind through the extern "C" boundary
+        return fail(B200_ERR_CUDA, "host error: %s", ex.what());
+    } catch (...) {
+        return fail(B200_ERR_CUDA, "unknown host error");
+    }
+}
+
 // ------------------------------------------------------------------------------
 // radix-2 domains: twiddle tables cached per (device, log n); coset tables per last shift g
 // ------------------------------------------------------------------------------

@@ -284,6 +284,46 @@ static __global__ void __launch_bounds__(128) k_fr_scale_inv_geometric(Fr *__res
     }
 }
 
+// out[i] = in[i] * a0 * a_ratio^i / prod_f (c1_f * ratio_f^i - c0_f), i < n, f < nf (1 or 2); in == nullptr: in[i] = 1.
+// The per-point divisions of libfqfft's Lagrange evaluations, _basic_radix2_evaluate_all_lagrange_polynomials
+// (FQFFT/evaluation_domain/domains/basic_radix2_domain_aux.tcc:225-233: u[i] = l * (t - r).inverse(), l *= omega, r *= omega)
+// and step_radix2_domain::evaluate_all_lagrange_polynomials (step_radix2_domain.tcc:171-176), one Fp inversion per point on the
+// host there.  Same run structure as k_fr_scale_inv_geometric; the numerator rides in the prefix products.
+// consts: a0, a_ratio, then (c1, ratio, c0) per factor.
+static __global__ void __launch_bounds__(128) k_fr_geometric_quotients(const Fr *in, Fr *out /* may alias in */, size_t n,
+                                                                       const Fr *__restrict__ consts, int nf)
+{
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * INVG_RUN;
+    if (i0 >= n) return;
+    const Fr a_ratio = consts[1], r1 = consts[3], z1 = consts[4];
+    const Fr r2 = nf > 1 ? consts[6] : Fr::one(), z2 = nf > 1 ? consts[7] : Fr::zero();
+    const uint32_t cnt = (uint32_t)min((size_t)INVG_RUN, n - i0);
+    Fr den[INVG_RUN], pre[INVG_RUN];
+    Fr num = Fr::mul(consts[0], fr_pow(a_ratio, i0));
+    Fr t1 = Fr::mul(consts[2], fr_pow(r1, i0));
+    Fr t2 = nf > 1 ? Fr::mul(consts[5], fr_pow(r2, i0)) : Fr::one();
+    Fr acc = Fr::one();
+#pragma unroll 1
+    for (uint32_t k = 0; k < cnt; k++) {
+        Fr d = Fr::sub(t1, z1);
+        if (nf > 1) d = Fr::mul(d, Fr::sub(t2, z2));
+        den[k] = d;
+        pre[k] = Fr::mul(acc, num);
+        acc = Fr::mul(acc, d);
+        num = Fr::mul(num, a_ratio);
+        t1 = Fr::mul(t1, r1);
+        if (nf > 1) t2 = Fr::mul(t2, r2);
+    }
+    Fr inv = Fr::inv(acc);
+#pragma unroll 1
+    for (int k = (int)cnt - 1; k >= 0; k--) {
+        Fr q = Fr::mul(inv, pre[k]);
+        inv = Fr::mul(inv, den[k]);
+        if (in) q = Fr::mul(q, in[i0 + k]);
+        out[i0 + k] = q;
+    }
+}
+
 // x[i] = x[i] * y[i] - z[i], i < n: H on the coset before the division, r1cs_to_qap.tcc:270-300
 static __global__ void __launch_bounds__(256) k_fr_mul_sub(Fr *__restrict__ x, const Fr *__restrict__ y, const Fr *__restrict__ z, size_t n)
 {

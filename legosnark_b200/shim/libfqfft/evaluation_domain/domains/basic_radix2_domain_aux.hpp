@@ -14,6 +14,7 @@
 // transform with omega = get_root_of_unity(n) or its inverse goes to b200_fr_fft (modes 0 / 4);
 // other fields (libff::Double, other curves) and other roots keep the reference's template.
 // Scaling by 1/n, coset shifts and divide_by_Z_on_coset stay in the caller as the reference wrote them.
+// _basic_radix2_evaluate_all_lagrange_polynomials (one inversion per point in the reference) is re-pointed the same way.
 #ifndef B200_SHIM_BASIC_RADIX2_DOMAIN_AUX_HPP_
 #define B200_SHIM_BASIC_RADIX2_DOMAIN_AUX_HPP_
 
@@ -90,6 +91,35 @@ struct fft_dispatch<FieldT, true> {
     }
 };
 
+// _basic_radix2_evaluate_all_lagrange_polynomials (FQFFT/evaluation_domain/domains/basic_radix2_domain_aux.tcc:183-236): the
+// reference computes u[i] = l * (t - r).inverse() with ONE Fp inversion per domain point (:228-233); libsnark's generators reach it
+// through r1cs_to_qap_instance_map_with_evaluation (r1cs_to_qap.tcc:127-190).  Here the host forms l_0 = (t^m - 1) / m and the
+// device computes u[i] = l_0 omega^i / (t - omega^i) with batched inversions (b200_fr_geometric_quotients).  t on the domain itself
+// (t^m == 1) keeps the reference's search loop (:201-214), which divides nothing.
+template <typename FieldT, bool Fp4 = looks_like_fp4<FieldT>::value>
+struct lagrange_dispatch {
+    static std::vector<FieldT> run(const size_t m, const FieldT &t) { return _basic_radix2_evaluate_all_lagrange_polynomials(m, t); }
+};
+
+template <typename FieldT>
+struct lagrange_dispatch<FieldT, true> {
+    static std::vector<FieldT> run(const size_t m, const FieldT &t)
+    {
+        if (m < 2 || !is_bn254_fr<FieldT>()) return _basic_radix2_evaluate_all_lagrange_polynomials(m, t);
+        if (m != ((size_t)1 << libff::log2(m))) throw DomainSizeException("expected m == (1u << log2(m))");  // aux.tcc:190
+        const FieldT tm = t ^ m;
+        if (tm == FieldT::one()) return _basic_radix2_evaluate_all_lagrange_polynomials(m, t);
+        const FieldT omega = libff::get_root_of_unity<FieldT>(m);
+        // a0, a_ratio, then the factor (c1, ratio, c0): u[i] = a0 omega^i / (-omega^i + t)
+        const FieldT consts[5] = {(tm - FieldT::one()) * FieldT(m).inverse(), omega, -FieldT::one(), omega, -t};
+        std::vector<FieldT> u(m, FieldT::zero());
+        ensure_engine();
+        if (b200_fr_geometric_quotients(reinterpret_cast<uint64_t *>(u.data()), nullptr, m, reinterpret_cast<const uint64_t *>(consts), 1) != B200_OK)
+            throw std::runtime_error(std::string("b200_fr_geometric_quotients failed: ") + b200_last_error());
+        return u;
+    }
+};
+
 }  // namespace b200_detail
 
 template <typename FieldT>
@@ -98,10 +128,18 @@ void b200_radix2_FFT(std::vector<FieldT> &a, const FieldT &omega)
     b200_detail::fft_dispatch<FieldT>::run(a, omega);
 }
 
+template <typename FieldT>
+std::vector<FieldT> b200_radix2_lagrange(const size_t m, const FieldT &t)
+{
+    return b200_detail::lagrange_dispatch<FieldT>::run(m, t);
+}
+
 }  // namespace libfqfft
 
 // from here on the reference's call sites (basic / extended / step radix-2 domains) reach the engine
 #undef _basic_radix2_FFT
 #define _basic_radix2_FFT b200_radix2_FFT
+// (a function template in the reference, not a macro: the definition above this line keeps its name, the callers below get ours)
+#define _basic_radix2_evaluate_all_lagrange_polynomials b200_radix2_lagrange
 
 #endif  // B200_SHIM_BASIC_RADIX2_DOMAIN_AUX_HPP_

@@ -76,6 +76,42 @@ inline void step_radix2_domain<libff::Fr<libff::default_ec_pp>>::divide_by_Z_on_
         throw std::runtime_error(std::string("b200_fr_scale_inv_geometric failed: ") + b200_last_error());
 }
 
+// evaluate_all_lagrange_polynomials (step_radix2_domain.tcc:161-186): besides the two radix-2 Lagrange vectors (one inversion per
+// point each in the reference, served by the shadow of basic_radix2_domain_aux.hpp) the big half is multiplied by
+// L0 * (elt - omega^small_m).inverse() with one more inversion per point (:172-176).  Both denominators go to the device in one
+// call: result[i] = (l_0 L0) big_omega^i / ((t - big_omega^i) (rho^i - omega^small_m)), rho = big_omega^small_m.
+template <>
+inline std::vector<libff::Fr<libff::default_ec_pp>> step_radix2_domain<libff::Fr<libff::default_ec_pp>>::evaluate_all_lagrange_polynomials(
+    const libff::Fr<libff::default_ec_pp> &t)
+{
+    typedef libff::Fr<libff::default_ec_pp> FieldT;
+    std::vector<FieldT> result(this->m, FieldT::zero());
+    const FieldT L0 = (t ^ small_m) - (omega ^ small_m);
+    const FieldT omega_to_small_m = omega ^ small_m;
+    const FieldT big_omega_to_small_m = big_omega ^ small_m;
+    const FieldT t_big = t ^ big_m;
+    b200_detail::ensure_engine();
+    if (t_big == FieldT::one()) {
+        // t on the big domain: inner_big is the reference's unit vector (aux.tcc:201-214); the :172-176 loop as one device pass over it
+        const std::vector<FieldT> inner_big = _basic_radix2_evaluate_all_lagrange_polynomials(big_m, t);
+        const FieldT consts[5] = {L0, FieldT::one(), FieldT::one(), big_omega_to_small_m, omega_to_small_m};
+        if (b200_fr_geometric_quotients(reinterpret_cast<uint64_t *>(result.data()), reinterpret_cast<const uint64_t *>(inner_big.data()), big_m,
+                                        reinterpret_cast<const uint64_t *>(consts), 1) != B200_OK)
+            throw std::runtime_error(std::string("b200_fr_geometric_quotients failed: ") + b200_last_error());
+    } else {
+        const FieldT consts[8] = {(t_big - FieldT::one()) * FieldT(big_m).inverse() * L0, big_omega,        // numerator l_0 L0 big_omega^i
+                                  -FieldT::one(), big_omega, -t,                                                // t - big_omega^i
+                                  FieldT::one(), big_omega_to_small_m, omega_to_small_m};                       // rho^i - omega^small_m
+        if (b200_fr_geometric_quotients(reinterpret_cast<uint64_t *>(result.data()), nullptr, big_m, reinterpret_cast<const uint64_t *>(consts), 2) !=
+            B200_OK)
+            throw std::runtime_error(std::string("b200_fr_geometric_quotients failed: ") + b200_last_error());
+    }
+    const std::vector<FieldT> inner_small = _basic_radix2_evaluate_all_lagrange_polynomials(small_m, t * omega.inverse());  // :164
+    const FieldT L1 = ((t ^ big_m) - FieldT::one()) * ((omega ^ big_m) - FieldT::one()).inverse();                           // :178
+    for (size_t i = 0; i < small_m; ++i) result[big_m + i] = L1 * inner_small[i];
+    return result;
+}
+
 }  // namespace libfqfft
 #endif  // BN254 default curve
 

@@ -274,6 +274,16 @@ class Checker:
         self._lscall("fr_step_divide_z", _ptr(a), ctypes.c_size_t(log_big), ctypes.c_size_t(log_small))
         return a
 
+    def fr_lagrange(self, log_big, log_small, t):
+        """evaluate_all_lagrange_polynomials(t) of libfqfft's basic_radix2_domain (log_small None: 2^log_big points) or
+        step_radix2_domain (2^log_big + 2^log_small points)"""
+        t = _c(t, 4)
+        m = (1 << log_big) + (0 if log_small is None else 1 << log_small)
+        out = np.zeros((m, 4), dtype=np.uint64)
+        ls = ctypes.c_size_t(-1 if log_small is None else log_small)
+        self._lscall("fr_lagrange", _ptr(out), ctypes.c_size_t(log_big), ls, _ptr(t))
+        return out
+
     # -- sum-check tables (LS/prototools/mle.h, LS/gadgets/sumcheck.h) --------------------
     def fr_eq_table(self, r):
         r = _c(r, 4)

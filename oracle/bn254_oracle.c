@@ -853,6 +853,92 @@ int orc_fr_step_fft(uint64_t *a_, size_t log_big, size_t log_small, int mode, co
     return 0;
 }
 
+/* _basic_radix2_evaluate_all_lagrange_polynomials: FQFFT/evaluation_domain/domains/basic_radix2_domain_aux.tcc:183-236.
+ * u has m = 2^log_m entries; returns through u the values L_{i,S}(t) on S = {omega^i}. */
+static void fr_basic_lagrange(fp_t *u, size_t log_m, const fp_t *t)
+{
+    const size_t m = (size_t)1 << log_m;
+    if (m == 1) { /* :185-188 */
+        u[0] = FR.one;
+        return;
+    }
+    fp_t omega, tm;
+    fr_root_of_unity(&omega, log_m);
+    memset(u, 0, m * sizeof(fp_t));
+    fr_pow_u64(&tm, t, m);
+    if (memcmp(&tm, &FR.one, sizeof tm) == 0) { /* :201-214: t is a point of S */
+        fp_t omega_i = FR.one;
+        for (size_t i = 0; i < m; ++i) {
+            if (memcmp(&omega_i, t, sizeof omega_i) == 0) {
+                u[i] = FR.one;
+                return;
+            }
+            fr_mul(&omega_i, &omega_i, &omega);
+        }
+    }
+    fp_t Z, l, r = FR.one, mm, d; /* :225-233 */
+    const uint64_t mb[4] = {(uint64_t)m, 0, 0, 0};
+    fr_sub(&Z, &tm, &FR.one);
+    fp_from_bigint(&mm, mb, &FR);
+    fp_inv(&mm, &mm, &FR);
+    fr_mul(&l, &Z, &mm);
+    for (size_t i = 0; i < m; ++i) {
+        fr_sub(&d, t, &r);
+        fp_inv(&d, &d, &FR);
+        fr_mul(&u[i], &l, &d);
+        fr_mul(&l, &l, &omega);
+        fr_mul(&r, &r, &omega);
+    }
+}
+
+/* evaluate_all_lagrange_polynomials(t) of basic_radix2_domain (basic_radix2_domain.tcc:80-84; log_small == (size_t)-1) and of
+ * step_radix2_domain (step_radix2_domain.tcc:161-186; 2^log_big + 2^log_small points): what libsnark's generators call through
+ * r1cs_to_qap_instance_map_with_evaluation (r1cs_to_qap.tcc:127-190). */
+int orc_fr_lagrange(uint64_t *out_, size_t log_big, size_t log_small, const uint64_t *t_)
+{
+    fp_t *out = (fp_t *)out_, t;
+    memcpy(&t, t_, sizeof t);
+    if (log_big > 27) return 1;
+    if (log_small == (size_t)-1) {
+        fr_basic_lagrange(out, log_big, &t);
+        return 0;
+    }
+    if (log_small >= log_big) return 1;
+    const size_t big = (size_t)1 << log_big, small = (size_t)1 << log_small;
+    fp_t omega, big_omega, omega_inv, t_small;
+    fr_root_of_unity(&omega, log_big + 1); /* step_radix2_domain.tcc:31-33: omega, big_omega = omega^2 */
+    fr_mul(&big_omega, &omega, &omega);
+    fp_t *inner_big = (fp_t *)malloc(big * sizeof(fp_t)), *inner_small = (fp_t *)malloc(small * sizeof(fp_t));
+    if (!inner_big || !inner_small) return 1;
+    fr_basic_lagrange(inner_big, log_big, &t); /* :163 */
+    fp_inv(&omega_inv, &omega, &FR);
+    fr_mul(&t_small, &t, &omega_inv);
+    fr_basic_lagrange(inner_small, log_small, &t_small); /* :164 */
+    fp_t L0, w, rho, elt = FR.one, d, x; /* :168-176 */
+    fr_pow_u64(&w, &omega, small);
+    fr_pow_u64(&L0, &t, small);
+    fr_sub(&L0, &L0, &w);
+    fr_pow_u64(&rho, &big_omega, small);
+    for (size_t i = 0; i < big; ++i) {
+        fr_sub(&d, &elt, &w);
+        fp_inv(&d, &d, &FR);
+        fr_mul(&x, &inner_big[i], &L0);
+        fr_mul(&out[i], &x, &d);
+        fr_mul(&elt, &elt, &rho);
+    }
+    fp_t L1, den; /* :178-183 */
+    fr_pow_u64(&L1, &t, big);
+    fr_sub(&L1, &L1, &FR.one);
+    fr_pow_u64(&den, &omega, big);
+    fr_sub(&den, &den, &FR.one);
+    fp_inv(&den, &den, &FR);
+    fr_mul(&L1, &L1, &den);
+    for (size_t i = 0; i < small; ++i) fr_mul(&out[big + i], &L1, &inner_small[i]);
+    free(inner_big);
+    free(inner_small);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* wire format: point compression               */
 /* operator<< / operator>> of alt_bn128_G1 (alt_bn128_g1.cpp:404-459),  */

@@ -12,6 +12,7 @@
 //   ref_fr_beta_suffix    DPBeta's suffix table after precomputeAll (src/prototools/mle.h:130-150)
 //   ref_fr_step_fft       libfqfft step_radix2_domain   (libfqfft/evaluation_domain/domains/step_radix2_domain.tcc:38-152)
 //   ref_fr_step_divide_z  step_radix2_domain::divide_by_Z_on_coset (:213-241)
+//   ref_fr_lagrange       basic_radix2_domain / step_radix2_domain ::evaluate_all_lagrange_polynomials (basic_radix2_domain_aux.tcc:183-236, step_radix2_domain.tcc:161-186)
 //   ref_fr_fft            libfqfft basic_radix2_domain  (libfqfft/evaluation_domain/domains/basic_radix2_domain.tcc)
 // LegoSNARK compiles with CURVE=BN128 only: LFr = bn128 Fr, same Montgomery limbs as
 // alt_bn128's.
@@ -98,6 +99,23 @@ int ref_fr_step_divide_z(uint64_t *a, size_t log_big, size_t log_small)
     vector<LFr> v = load_fr(a, m);
     dom.divide_by_Z_on_coset(v);
     for (size_t i = 0; i < m; i++) store_fr(a + 4 * i, v[i]);
+    return 0;
+}
+
+// evaluate_all_lagrange_polynomials(t): basic_radix2_domain (log_small == (size_t)-1) or step_radix2_domain
+int ref_fr_lagrange(uint64_t *out, size_t log_big, size_t log_small, const uint64_t *t)
+{
+    init_once();
+    const LFr tt = load_fr(t, 1)[0];
+    vector<LFr> u;
+    if (log_small == (size_t)-1) {
+        libfqfft::basic_radix2_domain<LFr> dom((size_t)1 << log_big);
+        u = dom.evaluate_all_lagrange_polynomials(tt);
+    } else {
+        libfqfft::step_radix2_domain<LFr> dom(((size_t)1 << log_big) + ((size_t)1 << log_small));
+        u = dom.evaluate_all_lagrange_polynomials(tt);
+    }
+    for (size_t i = 0; i < u.size(); i++) store_fr(out + 4 * i, u[i]);
     return 0;
 }
 

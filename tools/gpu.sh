@@ -35,7 +35,7 @@ for step in "$@"; do
                python bench.py --steps 2 --warmup 3 --no-cpu-baseline "${A[@]:1}" > ${O}_ncu_${short}_run.log 2>&1
              ncu -i ${O}_ncu_$short.ncu-rep --page raw --csv > ${O}_ncu_${short}_raw.csv 2>/dev/null
              ncu -i ${O}_ncu_$short.ncu-rep --page details --csv > ${O}_ncu_${short}_details.csv 2>/dev/null ;;
-    integ)   ( time B200_GPUS=1 timeout 1500 integration/_ref/"${A[0]}" "${A[@]:1}" ) 2>&1 | grep -E '^\{|real|rror|terminate|what|fault' >> ${O}_integration.log ;;
+    integ)   ( time B200_GPUS=1 timeout 1500 integration/_ref/"${A[0]}" "${A[@]:1}" ) 2>&1 | grep -E '^\{|^\[b200\]|leave|real|rror|terminate|what|fault' >> ${O}_integration.log ;;
     *) echo "unknown step $step" >> ${O}_errors.log ;;
   esac
 done
