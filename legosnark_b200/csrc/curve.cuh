@@ -129,6 +129,37 @@ B200_HD void xyzz_madd(XYZZ<F> &acc, const F &x2, const F &y2_in, bool negate)
     acc.zzz = F::mul(acc.zzz, PPP);
 }
 
+// The same mixed addition with its independent products issued in pairs (Fp::mul2: alternating rows of two Montgomery products),
+// for base fields that have mul2 (Fq).  Same products, same result; option `g1_paired` of k_accumulate.
+template <class F>
+B200_HD void xyzz_madd_paired(XYZZ<F> &acc, const F &x2, const F &y2_in, bool negate)
+{
+    const F y2 = F::cneg(y2_in, negate);
+    if (acc.is_inf()) {
+        acc.x = x2;
+        acc.y = y2;
+        acc.zz = F::one();
+        acc.zzz = F::one();
+        return;
+    }
+    F U2, S2;
+    F::mul2(U2, S2, x2, acc.zz, y2, acc.zzz);
+    const F P = F::sub(U2, acc.x);
+    const F R = F::sub(S2, acc.y);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = xyzz_dbl_affine(x2, y2);
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    const F PP = F::sqr(P);
+    F PPP, Q;
+    F::mul2(PPP, Q, P, PP, acc.x, PP);
+    const F X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+    acc.y = F::mul_sub(R, F::sub(Q, X3), acc.y, PPP);
+    acc.x = X3;
+    F::mul2(acc.zz, acc.zzz, acc.zz, PP, acc.zzz, PPP);
+}
+
 template <class F>
 B200_COLD void xyzz_dbl_cold(XYZZ<F> *p);
 

@@ -176,6 +176,10 @@ extern uint64_t g_next_handle;
 extern b200_stats_t g_stats;
 extern int g_tune_c, g_tune_L, g_tune_chunks, g_tune_logS, g_tune_split, g_tune_pre, g_tune_ones, g_tune_host_horner;
 extern int g_tune_marginals;  // 1: one-window reduction by marginal sums (measured: no faster, profiles/r2c); 0 (default): bit decomposition over all segments
+extern int g_tune_g2blocks;  // k_accumulate<Fq2> builds: 1 (default) ptxas may use 255 registers (252 used, two blocks per SM; 3 % faster), 2: 190 registers (round 1), 3: 168 registers + spills, three blocks per SM (5 % slower); profiles/r4f_stage.jsonl
+extern int g_tune_red_block;  // threads per block of k_reduce_segments (32, 64, 96 or 128)
+extern int g_tune_g1paired;  // k_accumulate<Fq> with the mixed addition's independent products issued in pairs: 1 (ptxas picks the registers), 2 (four blocks per SM)
+extern int g_tune_quads;  // 1 (default): stage 2 of the window reduction with quad-cooperative additions (k_reduce_bits_quad); 0: one thread per partial sum
 extern int g_tune_g2pair;  // 1: G2 accumulation with two lanes per task (measured 5 % slower: profiles/r2n_g2_lane_pairs.jsonl); 0 (default): one thread per task
 extern int g_tune_even_chunks;  // 1 (default): equal upload chunks; 0: short first chunk (measured: no gain)
 extern int g_tune_ba;    // batch-affine tree levels in front of the XYZZ accumulation: 0 (off), 1 or 2

@@ -40,7 +40,7 @@ std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1, g_tune_host_horner = 1;
-int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 0, g_tune_even_chunks = 1;
+int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 0, g_tune_even_chunks = 1, g_tune_g2blocks = 1, g_tune_red_block = 128, g_tune_g1paired = 0, g_tune_quads = 1;
 bool g_scalars_resident = false;
 
 static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal
@@ -188,6 +188,10 @@ static int apply_tuning(const std::string &k, int value)
     else if (k == "host_horner") g_tune_host_horner = value;  // 0: the device also weights and sums the per-job results of a one-window reduction
     else if (k == "reduce_marginals") g_tune_marginals = value;  // 0: bit decomposition over all segments (round 1)
     else if (k == "batch_affine") g_tune_ba = std::min(std::max(value, 0), 2);  // tree levels of affine pair additions before the XYZZ tail
+    else if (k == "reduce_block") g_tune_red_block = value;  // threads per block of k_reduce_segments
+    else if (k == "reduce_quads") g_tune_quads = value;       // 0: one thread per partial sum in stage 2 of the window reduction (k_reduce_bits)
+    else if (k == "g1_paired") g_tune_g1paired = value;      // 1 / 2: paired products in k_accumulate<Fq> (2: compiled for four blocks per SM)
+    else if (k == "g2_blocks") g_tune_g2blocks = value;      // 3: the 168-register build of k_accumulate<Fq2> (three blocks per SM)
     else if (k == "g2_lane_pairs") g_tune_g2pair = value;    // 0: k_accumulate<Fq2> with one thread per task
     else if (k == "even_chunks") g_tune_even_chunks = value;  // 0: short first upload chunk (measured: no gain, profiles/r2w_e2e_chunk_probe.jsonl)
     else if (k == "partition_sort") g_tune_sort = value;     // 0: the round-1 global-atomics counting sort

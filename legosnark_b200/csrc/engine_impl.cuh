@@ -208,6 +208,13 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     // (precomputed key) spreads each job over 8-16 blocks
     P.split = RED2_SPLIT;
     if (g.Wb == 1) P.split = P.M <= (1u << 14) ? 8 : 16;  // swept: profiles/r15b_reduce_sweep_*.jsonl
+    if (g_tune_quads) {
+        // quad-cooperative stage 2 (k_reduce_bits_quad): a block is 32 partial sums instead of 128; as many blocks per job as one
+        // wave of the machine holds (four blocks of 128 lanes per SM), but at least one element per quad
+        const uint32_t wave = (uint32_t)D.sms * 4u, per_window = std::max(1u, wave / std::max(1u, g.Wb));
+        P.split = std::max(1u, std::min(per_window / (P.njobs + 1), std::max(1u, (P.M >> 1) / 32u)));
+        P.split = std::min(P.split, 64u);
+    }
     if (g_tune_split > 0) P.split = (uint32_t)std::min(g_tune_split, 64);
     if (g.Wb == 1 && !dense && g_tune_host_horner) {  // one window: per-job sums to the host (MsmGeom::red_jobs)
         P.g.red_jobs = P.njobs;
@@ -333,6 +340,19 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
                (const uint32_t *)totals, partial, tbk, seed);
     } else if (sizeof(F) == 64 && g_tune_g2pair) {
         launch_accumulate_g2pair(D, st, d_aff, entries, meta, order, totals, partial, tbk, seed, max_tasks);
+    } else if (sizeof(F) == 32 && g_tune_g1paired) {  // independent products of the mixed addition issued in pairs
+        if (g_tune_g1paired == 2)
+            LAUNCH(D, (k_accumulate<F, (sizeof(F) == 32 ? 4 : 0), sizeof(F) == 32>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order,
+                   totals, partial, tbk, seed);
+        else
+            LAUNCH(D, (k_accumulate<F, 0, sizeof(F) == 32>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk,
+                   seed);
+    } else if (sizeof(F) == 64 && g_tune_g2blocks == 1) {  // ptxas free to use 255 registers (252 used), two blocks per SM
+        LAUNCH(D, (k_accumulate<F, (sizeof(F) == 64 ? 1 : 0)>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial,
+               tbk, seed);
+    } else if (sizeof(F) == 64 && g_tune_g2blocks == 3) {
+        LAUNCH(D, (k_accumulate<F, (sizeof(F) == 64 ? 3 : 0)>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial,
+               tbk, seed);
     } else {
         LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk, seed);
     }
@@ -365,7 +385,10 @@ void enqueue_reduce(Device &D, cudaStream_t st, const MsmPlan &P, bool dense)
 {
     const MsmGeom &g = P.g;
     XYZZ<F> *seg_run = D.seg_run.as<XYZZ<F>>(), *seg_acc = D.seg_acc.as<XYZZ<F>>(), *wsums = D.window_sums.as<XYZZ<F>>();
-    LAUNCH(D, (k_reduce_segments<F>), cdiv(P.nseg, RED_THREADS), RED_THREADS, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(),
+    // block size of stage 1: small blocks spread a grid of a few hundred warps evenly over the SMs (1024 blocks of 32 threads on
+    // 148 SMs: 7 or 6 per SM; 256 blocks of 128: 2 or 1)
+    const uint32_t rb = (uint32_t)std::min(std::max(g_tune_red_block, 32), RED_THREADS) & ~31u;
+    LAUNCH(D, (k_reduce_segments<F>), cdiv(P.nseg, rb), rb, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(),
            D.partial.as<XYZZ<F>>(), dense ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr, g, P.logS, seg_run, seg_acc);
     const uint32_t nres = result_points(g);
     if (g.red_hb) {
@@ -374,6 +397,10 @@ void enqueue_reduce(Device &D, cudaStream_t st, const MsmPlan &P, bool dense)
                g.red_hb, g.red_lb, D.job_out.as<XYZZ<F>>());
         LAUNCH(D, (k_reduce_marginal_bits<F>), nres, MARG_THREADS, 0, st, (const XYZZ<F> *)D.job_out.as<XYZZ<F>>(), g.red_hb, g.red_lb, wsums);
     } else
+    if (g_tune_quads)
+        LAUNCH(D, (k_reduce_bits_quad<F>), dim3((P.njobs + 1) * P.split, g.Wb), RED2_THREADS, 0, st, seg_run, seg_acc, P.M, P.logS,
+               P.split, g.red_jobs ? 1u : 0u, D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
+    else
     LAUNCH(D, (k_reduce_bits<F>), dim3((P.njobs + 1) * P.split, g.Wb), RED2_THREADS, 0, st, seg_run, seg_acc, P.M, P.logS,
            P.split, g.red_jobs ? 1u : 0u, D.job_out.as<XYZZ<F>>(), D.done.as<uint32_t>(), wsums);
     CK(cudaMemcpyAsync(D.h_pinned, wsums, (size_t)nres * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));

@@ -358,6 +358,56 @@ struct alignas(16) Fp {
     // a b - c d
     B200_HD static Fp mul_sub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return mul_add(a, b, neg(c), d); }
 
+    // Two INDEPENDENT products r0 = a0 b0, r1 = a1 b1 with their operand-scanning rows alternating in the instruction stream.
+    // A product is a chain of dependent carry rows (row i + 1 needs row i's even[0] for the quotient digit); a warp that runs one
+    // product at a time stalls on that chain whenever its scheduler has no other warp to issue (k_accumulate<Fq2>: two warps per
+    // scheduler, `wait` is the top stall).  With the rows of two products adjacent ptxas overlaps the tail of one with the head of
+    // the other.  Same instructions, same results.
+    B200_HD static void mul2(Fp &r0, Fp &r1, const Fp &a0, const Fp &b0, const Fp &a1, const Fp &b1)
+    {
+        uint32_t e0[8], o0[8], e1[8], o1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            detail::mont_step<P>(e0, o0, a0.l, b0.l[i], i == 0);
+            detail::mont_step<P>(e1, o1, a1.l, b1.l[i], i == 0);
+            detail::mont_step<P>(o0, e0, a0.l, b0.l[i + 1], false);
+            detail::mont_step<P>(o1, e1, a1.l, b1.l[i + 1], false);
+        }
+        r0.l[0] = add_cc(e0[0], o0[1]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) r0.l[k] = addc_cc(e0[k], o0[k + 1]);
+        r0.l[7] = addc(e0[7], 0u);
+        r1.l[0] = add_cc(e1[0], o1[1]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) r1.l[k] = addc_cc(e1[k], o1[k + 1]);
+        r1.l[7] = addc(e1[7], 0u);
+        detail::final_sub<P>(r0.l);
+        detail::final_sub<P>(r1.l);
+    }
+    // r0 = a0 b0 + c0 d0, r1 = a1 b1 + c1 d1: two fused two-product passes (mul_add) with alternating rows
+    B200_HD static void mul_add2(Fp &r0, Fp &r1, const Fp &a0, const Fp &b0, const Fp &c0, const Fp &d0, const Fp &a1, const Fp &b1,
+                                 const Fp &c1, const Fp &d1)
+    {
+        uint32_t e0[8], o0[8], e1[8], o1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            detail::mont_step2<P>(e0, o0, a0.l, b0.l[i], c0.l, d0.l[i], i == 0);
+            detail::mont_step2<P>(e1, o1, a1.l, b1.l[i], c1.l, d1.l[i], i == 0);
+            detail::mont_step2<P>(o0, e0, a0.l, b0.l[i + 1], c0.l, d0.l[i + 1], false);
+            detail::mont_step2<P>(o1, e1, a1.l, b1.l[i + 1], c1.l, d1.l[i + 1], false);
+        }
+        r0.l[0] = add_cc(e0[0], o0[1]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) r0.l[k] = addc_cc(e0[k], o0[k + 1]);
+        r0.l[7] = addc(e0[7], 0u);
+        r1.l[0] = add_cc(e1[0], o1[1]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) r1.l[k] = addc_cc(e1[k], o1[k + 1]);
+        r1.l[7] = addc(e1[7], 0u);
+        detail::final_sub<P>(r0.l);
+        detail::final_sub<P>(r1.l);
+    }
+
     // a/R mod p: Fp_model::as_bigint() (fp.tcc:227-238) — Montgomery product with the integer 1.
     B200_HD static Fp from_mont(const Fp &a)
     {
@@ -453,14 +503,28 @@ struct Fq2 {
     {
         // same value as the three-product Karatsuba form; each coordinate is one fused
         // two-product Montgomery pass (2 x 200 multiply-adds instead of 3 x 136)
+#if defined(B200_FQ2_INTERLEAVED_PRODUCTS)
+        // the two coordinates are independent: their rows alternate (Fq::mul_add2).  Measured on k_accumulate<Fq2> at 2^20
+        // (profiles/r4g_stage.jsonl): 6.45 ms against 6.37 ms for the two passes one after the other -> off.
+        Fq2 r;
+        Fq::mul_add2(r.c0, r.c1, x.c0, y.c0, Fq::neg(x.c1), y.c1, x.c0, y.c1, x.c1, y.c0);
+        return r;
+#else
         return Fq2{Fq::mul_sub(x.c0, y.c0, x.c1, y.c1), Fq::mul_add(x.c0, y.c1, x.c1, y.c0)};
+#endif
     }
     // complex squaring, fp2.tcc:111-120
     B200_HD static Fq2 sqr(const Fq2 &x)
     {
+#if defined(B200_FQ2_INTERLEAVED_PRODUCTS)
+        Fq ab, c0;
+        Fq::mul2(ab, c0, x.c0, x.c1, Fq::add(x.c0, x.c1), Fq::sub(x.c0, x.c1));
+        return Fq2{c0, Fq::dbl(ab)};
+#else
         const Fq ab = Fq::mul(x.c0, x.c1);
         const Fq c0 = Fq::mul(Fq::add(x.c0, x.c1), Fq::sub(x.c0, x.c1));
         return Fq2{c0, Fq::dbl(ab)};
+#endif
     }
     B200_HD static Fq2 mul_sub(const Fq2 &a, const Fq2 &b, const Fq2 &c, const Fq2 &d) { return sub(mul(a, b), mul(c, d)); }
     B200_HD static Fq2 add(const Fq2 &a, const Fq2 &b) { return Fq2{Fq::add(a.c0, b.c0), Fq::add(a.c1, b.c1)}; }

@@ -517,8 +517,9 @@ static __global__ void __launch_bounds__(256) k_task_order(const uint2 *__restri
 }
 
 // one thread per task, longest tasks first
-template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
+// MINB: resident blocks per SM asked of ptxas (G2 only: 3 caps the kernel at 168 registers; knob `g2_blocks`)
+template <class F, int MINB = 0, bool PAIRED = false>
+__global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
                                                      const uint2 *__restrict__ meta, const uint32_t *__restrict__ order,
                                                      const uint32_t *__restrict__ totals, XYZZ<F> *__restrict__ partial,
                                                      const uint32_t *__restrict__ task_bucket, const XYZZ<F> *__restrict__ seed)
@@ -545,7 +546,8 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict_
                 cur = e[k + 1];
                 p = bases[cur & 0x7fffffffu];
             }
-            xyzz_madd(acc, q.x, q.y, neg != 0);
+            if constexpr (PAIRED) xyzz_madd_paired(acc, q.x, q.y, neg != 0);
+            else xyzz_madd(acc, q.x, q.y, neg != 0);
         }
     } else {
         // G2: accumulator (64 registers) + one point (32) + the product temporaries already fill the
@@ -717,9 +719,124 @@ __device__ __forceinline__ XYZZ<F> warp_sum_point(XYZZ<F> v, int width = 32)
 #pragma unroll 1
     for (int o = width >> 1; o > 0; o >>= 1) {
         const XYZZ<F> other = shfl_down_point(v, o);
-        xyzz_add_cold(&v, &other);
+        // lanes at or above o get their own value back from the shuffle: adding it would send them through the doubling
+        // path, which the whole warp then waits for at every level
+        if ((int)(threadIdx.x & 31u) < o) xyzz_add_cold(&v, &other);
     }
     return v;  // lane 0 holds the sum
+}
+
+// ------------------------------------------------------------------------------
+// Quad-cooperative addition.  The window reduction and every tree sum are chains of DEPENDENT point additions on
+// warps that have their scheduler to themselves: a lone warp needs 5-7 us for the 14 products of one XYZZ addition,
+// one after the other.  Here the four lanes of a quad (lane & ~3 .. lane | 3) hold the SAME accumulator and the SAME
+// operand (replicated) and split the products of add-2008-s over four levels:
+//     level 1   U1 = X1 ZZ2      U2 = X2 ZZ1      S1 = Y1 ZZZ2      S2 = Y2 ZZZ1        (all-gather; P, R on every lane)
+//     level 2   PP = P^2         RR = R^2         ZZ12 = ZZ1 ZZ2    ZZZ12 = ZZZ1 ZZZ2   (PP to all, RR to lane 1)
+//     level 3   PPP = P PP       Q = U1 PP        ZZ3 = ZZ12 PP     --                  (PPP to all)
+//     level 4   V = S1 PPP       T = R (Q - X3)   --                ZZZ3 = ZZZ12 PPP    (Y3 = T - V on lane 1; all-gather)
+// i.e. the depth of 4 products instead of 14, for ~90 shuffles.  Same products as xyzz_add, so the same coordinates
+// (bit for bit) on every lane.  All branches are uniform within a quad because the state is replicated.
+// ------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ F quad_bcast(const F &v, int src, uint32_t qmask)
+{
+    F r;
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(&v);
+    uint32_t *d = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_sync(qmask, a[i], src, 4);
+    return r;
+}
+
+template <class F>
+__device__ __noinline__ void xyzz_add_quad(XYZZ<F> *acc_, const XYZZ<F> *q_)
+{
+    XYZZ<F> &acc = *acc_;
+    const XYZZ<F> &q = *q_;
+    if (q.is_inf()) return;
+    if (acc.is_inf()) {
+        acc = q;
+        return;
+    }
+    const uint32_t ql = threadIdx.x & 3u;
+    const uint32_t qmask = 0xfu << ((threadIdx.x & 31u) & ~3u);
+    // level 1
+    F m1;
+    {
+        const F a = ql == 0 ? acc.x : ql == 1 ? q.x : ql == 2 ? acc.y : q.y;
+        const F b = ql == 0 ? q.zz : ql == 1 ? acc.zz : ql == 2 ? q.zzz : acc.zzz;
+        m1 = F::mul(a, b);
+    }
+    const F U1 = quad_bcast(m1, 0, qmask), U2 = quad_bcast(m1, 1, qmask), S1 = quad_bcast(m1, 2, qmask), S2 = quad_bcast(m1, 3, qmask);
+    const F P = F::sub(U2, U1);
+    const F R = F::sub(S2, S1);
+    if (P.is_zero()) {
+        if (R.is_zero()) xyzz_dbl_cold(&acc);  // the same point: every lane doubles its copy
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    // level 2: P^2, R^2 (as plain products: one convergent routine for the quad; the value is the same) and ZZ12, ZZZ12
+    F m2;
+    {
+        const F a = ql == 0 ? P : ql == 1 ? R : ql == 2 ? acc.zz : acc.zzz;
+        const F b = ql == 0 ? P : ql == 1 ? R : ql == 2 ? q.zz : q.zzz;
+        m2 = F::mul(a, b);
+    }
+    const F PP = quad_bcast(m2, 0, qmask);
+    // level 3 (lane 3 has nothing to do: it repeats lane 2's product to stay convergent)
+    F m3;
+    {
+        const F a = ql == 0 ? P : ql == 1 ? U1 : m2;  // lanes 2, 3: ZZ12 resp. ZZZ12 (lane 3's result is not used)
+        m3 = F::mul(a, PP);
+    }
+    const F PPP = quad_bcast(m3, 0, qmask);
+    // level 4
+    F X3 = F::zero(), m4;
+    {
+        F a, b;
+        if (ql == 1) {  // m2 = RR, m3 = Q
+            X3 = F::sub(F::sub(m2, PPP), F::dbl(m3));
+            a = R;
+            b = F::sub(m3, X3);
+        } else {
+            a = ql == 0 ? S1 : m2;  // lane 3: ZZZ12; lane 2 repeats a product it does not need
+            b = PPP;
+        }
+        m4 = F::mul(a, b);
+    }
+    const F V = quad_bcast(m4, 0, qmask);
+    const F Y3 = F::sub(m4, V);  // meaningful on lane 1
+    acc.x = quad_bcast(X3, 1, qmask);
+    acc.y = quad_bcast(Y3, 1, qmask);
+    acc.zz = quad_bcast(m3, 2, qmask);
+    acc.zzz = quad_bcast(m4, 3, qmask);
+}
+
+// sum over the eight quads of a warp (every quad holds its value replicated); quad 0 ends up with the warp's sum
+template <class F>
+__device__ __forceinline__ XYZZ<F> warp_sum_quads(XYZZ<F> v, int quads = 8)
+{
+#pragma unroll 1
+    for (int o = quads >> 1; o > 0; o >>= 1) {
+        const XYZZ<F> other = shfl_down_point(v, o * 4);
+        if ((int)((threadIdx.x & 31u) >> 2) < o) xyzz_add_quad(&v, &other);  // the other quads would add a value to itself
+    }
+    return v;
+}
+// sum over all quads of a block of 128 threads; the first quad of the block holds the result
+template <class F>
+__device__ __forceinline__ XYZZ<F> block_sum_quads(XYZZ<F> v, XYZZ<F> *sm)
+{
+    v = warp_sum_quads(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t qd = threadIdx.x >> 2;
+        v = qd < (blockDim.x >> 5) ? sm[qd] : XYZZ<F>::inf();
+        v = warp_sum_quads(v, (int)(blockDim.x >> 5));
+    }
+    return v;
 }
 
 // buckets that were split into 2..BIG_TASKS tasks (listed by k_task_meta): their task partials are
@@ -859,7 +976,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_segments(const uint32_t 
                                                                   MsmGeom g, uint32_t logS, XYZZ<F> *__restrict__ seg_run,
                                                                   XYZZ<F> *__restrict__ seg_acc)
 {
-    const uint32_t seg = blockIdx.x * RED_THREADS + threadIdx.x;  // global segment index over all windows
+    const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;  // global segment index over all windows (blocks of 32..RED_THREADS)
     const uint32_t nseg = g.NB >> logS;
     if (seg >= nseg) return;
     const uint32_t b0 = seg << logS;  // segments never straddle windows: S divides B
@@ -1100,6 +1217,62 @@ __global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits(const XYZZ<F> *__r
     if (threadIdx.x == 0) {
         window_sums[k] = v;
         done[k] = 0;  // ready for the next call
+    }
+}
+
+// k_reduce_bits with one QUAD per partial sum (xyzz_add_quad): same jobs, same block / ticket structure, a third of the
+// latency per addition.  A block of 128 lanes is 32 quads; quad j of part p takes the elements p * 32 + j, + nparts * 32, ...
+template <class F>
+__global__ void __launch_bounds__(RED2_THREADS) k_reduce_bits_quad(const XYZZ<F> *__restrict__ seg_run, const XYZZ<F> *__restrict__ seg_acc,
+                                                                    uint32_t M, uint32_t logS, uint32_t split, uint32_t per_job,
+                                                                    XYZZ<F> *__restrict__ job_out, uint32_t *__restrict__ done,
+                                                                    XYZZ<F> *__restrict__ window_sums)
+{
+    constexpr uint32_t NQ = RED2_THREADS / 4;
+    __shared__ XYZZ<F> sm[RED2_THREADS / 32];
+    __shared__ uint32_t ticket;
+    const uint32_t nout = gridDim.x, k = blockIdx.y, quad = threadIdx.x >> 2;
+    const uint32_t job = blockIdx.x < 2 * split ? 0 : blockIdx.x / split - 1;
+    const uint32_t nparts = job == 0 ? 2 * split : split;
+    const uint32_t part = job == 0 ? blockIdx.x : blockIdx.x % split;
+    const XYZZ<F> *src = (job == 0 ? seg_acc : seg_run) + (size_t)k * M;
+    const uint32_t count = job == 0 ? M : M >> 1;
+    const uint32_t bit = job == 0 ? 0 : job - 1;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = part * NQ + quad; i < count; i += nparts * NQ) {
+        const uint32_t s0 = job == 0 ? i : (((i >> bit) << (bit + 1)) | (1u << bit) | (i & ((1u << bit) - 1u)));
+        const XYZZ<F> q = src[s0];
+        xyzz_add_quad(&acc, &q);
+    }
+    acc = block_sum_quads(acc, sm);
+    if (threadIdx.x == 0) {
+        if (job > 0 && !per_job)
+            for (uint32_t i = 0; i < bit + logS; i++) xyzz_dbl_cold(&acc);
+        job_out[(size_t)k * nout + blockIdx.x] = acc;
+        __threadfence();
+        ticket = atomicAdd(&done[per_job ? job : k], 1u);
+    }
+    __syncthreads();
+    const uint32_t last = per_job ? nparts - 1 : nout - 1;
+    if (ticket != last) return;
+    // last block of the job (one window) or of window k: sum the partials, a quad per stride
+    __threadfence();
+    const uint32_t first = per_job ? (job == 0 ? 0 : (job + 1) * split) : 0;
+    const uint32_t total = per_job ? nparts : nout;
+    const XYZZ<F> *part_out = job_out + (per_job ? 0 : (size_t)k * nout) + first;
+    XYZZ<F> v = XYZZ<F>::inf();
+    for (uint32_t o = quad; o < total; o += NQ) {
+        const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(&part_out[o]);
+        XYZZ<F> q;
+        uint32_t *d = reinterpret_cast<uint32_t *>(&q);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = p[i];
+        xyzz_add_quad(&v, &q);
+    }
+    v = block_sum_quads(v, sm);  // sm is free again: all threads passed the barrier above
+    if (threadIdx.x == 0) {
+        window_sums[per_job ? job : k] = v;
+        done[per_job ? job : k] = 0;  // ready for the next call
     }
 }
 

@@ -340,6 +340,53 @@ def test_g2_lane_pairs(engine, orc, golden):
         key.close()
 
 
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_alternative_kernels_under_their_knobs(engine, orc, golden, grp):
+    """Kernels that stay in the tree as measured options must give the same group element as the defaults: stage 2 of the window
+    reduction with one thread per partial sum (`reduce_quads` = 0; the default is the quad-cooperative adder), the mixed addition
+    with paired products (`g1_paired`), the other register budgets of k_accumulate<Fq2> (`g2_blocks` = 2, 3), smaller blocks in
+    stage 1 (`reduce_block`).  Edge-case fixtures under forced geometries (P == Q and P == -Q inside the adders, zero bases),
+    uniform / skewed scalars on plain and precomputed keys."""
+    g = golden("msm_" + grp)
+    n = 3000
+    P, _ = inputs.bases(orc, grp, n, seed=861, affine=False)
+    P[7] = P[6]
+    P[9] = inputs.negate(orc, grp, P[8:9])[0]
+    P[11] = inputs.zero_point(grp)
+    s = inputs.fr_uniform(orc, n, seed=862)
+    s[6:10] = s[6]
+    cases = {"uniform": s, "heavy01": inputs.fr_zero_one_heavy(orc, n, seed=863), "equal": np.tile(s[3], (n, 1))}
+    want = {name: orc.msm(grp, P, v, chunks=orc.max_threads(), variant=1) for name, v in cases.items()}
+    knobs = [("reduce_quads", 0, 1), ("reduce_block", 32, 128)]
+    knobs += [("g1_paired", 1, 0)] if grp == "g1" else [("g2_blocks", 2, 1), ("g2_blocks", 3, 1)]
+    key = engine.CommitmentKey(grp, P)
+    pre = engine.CommitmentKey(grp, P)
+    pre.precompute(8)
+    try:
+        for knob, value, default in knobs:
+            engine.set_tuning_ex(knob, value)
+            try:
+                for c, L in ((0, 0), (5, 32), (11, 0)):
+                    engine.set_tuning(c, L)
+                    for name, v in cases.items():
+                        assert (key.multi_exp(v) == want[name]).all(), (knob, value, c, L, name)
+                    if c:
+                        for name in g["names"]:
+                            B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
+                            assert (engine.multi_exp(grp, B, S) == R).all(), (knob, value, name, c, L)
+                engine.set_tuning(0, 0)
+                engine.set_tuning_ex("use_precomputed", 2)
+                for name, v in cases.items():
+                    assert (pre.multi_exp(v) == want[name]).all(), (knob, value, "precomputed", name)
+            finally:
+                engine.set_tuning_ex(knob, default)
+                engine.set_tuning_ex("use_precomputed", 1)
+                engine.set_tuning(0, 0)
+    finally:
+        key.close()
+        pre.close()
+
+
 def _device_bases(engine, orc, grp, k):
     """P_i = k_i G made by the GPU fixed-base path, spot-checked against the oracle."""
     n = len(k)
