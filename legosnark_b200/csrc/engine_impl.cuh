@@ -32,7 +32,7 @@ inline double geometry_cost(size_t n, uint32_t c, bool pre)
 }
 
 // pre_c != 0: geometry of a precomputed key (window bits fixed when the key was extended)
-inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride = 0, uint32_t pre_off = 0)
+inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride = 0, uint32_t pre_off = 0, bool wide_field = false)
 {
     MsmGeom g;
     uint32_t best_c = 4;
@@ -80,7 +80,11 @@ inline MsmGeom choose_geometry(size_t n, uint32_t pre_c = 0, uint32_t pre_stride
         // ... unless the buckets themselves are already that many tasks (one task per bucket needs no combine)
         const double want_tasks = 148.0 * 512.0 * 6.0;
         const double cap = (double)n * g.W / want_tasks;
-        while (pre_c && (double)g.NB < want_tasks && L > 32 && L > cap) L >>= 1;
+        // G2 keeps 256 threads per SM resident and pays three times as much for every combine: once the buckets alone are a
+        // wave and a half of tasks they stay whole (2^18, c = 17: 2.97 -> 2.70 ms, profiles/r4r_stage_task_len.jsonl; G1 at
+        // the same size has 0.86 waves of buckets and prefers the split, 1.01 vs 1.10 ms)
+        const bool whole_buckets = wide_field && (double)g.NB >= 1.5 * 148.0 * 256.0;
+        while (pre_c && !whole_buckets && (double)g.NB < want_tasks && L > 32 && L > cap) L >>= 1;
         g.L = L;
     }
     return g;
@@ -167,7 +171,7 @@ template <class F>
 MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool dense, const MsmGeom *forced = nullptr)
 {
     MsmPlan P;
-    const MsmGeom g = P.g = forced ? *forced : choose_geometry(n);
+    const MsmGeom g = P.g = forced ? *forced : choose_geometry(n, 0, 0, 0, sizeof(F) == 64);
     P.max_entries = (size_t)g.W * chunk_max;
     if (P.max_entries >= (1ull << 32)) throw CudaError{"MSM shard too large: W * n must stay below 2^32 entries"};
     P.max_tasks = P.max_entries / g.L + g.NB;
@@ -878,7 +882,7 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
             bool pre = S.d_pre && g_tune_pre && g_tune_c == 0 && P.cnt > SMALL_MAX_N;
             if (pre && g_tune_pre != 2) pre = precomputed_pays(P.cnt, S.pre_c);  // 2 = always (tests)
             if (pre) {
-                const MsmGeom gp = choose_geometry(P.cnt, S.pre_c, (uint32_t)S.count, (uint32_t)(P.lo - S.begin));
+                const MsmGeom gp = choose_geometry(P.cnt, S.pre_c, (uint32_t)S.count, (uint32_t)(P.lo - S.begin), sizeof(F) == 64);
                 geoms[pi] = enqueue_msm<F>(D, st, reinterpret_cast<const Affine<F> *>(S.d_pre), S.d_flags + (P.lo - S.begin), ds,
                                            P.cnt, &gp);
             } else {
