@@ -48,12 +48,32 @@ struct CudaError {
 // ------------------------------------------------------------------------------
 // device context
 // ------------------------------------------------------------------------------
+// B200_TRACE=1 (engine_core.cu): host-side stalls above 1 ms inside a call -- buffer growth, a kernel's first launch (CUDA loads
+// its code then) -- are reported on stderr next to the per-call lines
+extern bool g_trace;
+struct TraceStall {
+    const char *what;
+    size_t arg;
+    std::chrono::steady_clock::time_point t0;
+    TraceStall(const char *w, size_t a) : what(w), arg(a)
+    {
+        if (g_trace) t0 = std::chrono::steady_clock::now();
+    }
+    ~TraceStall()
+    {
+        if (!g_trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms >= 1.0) fprintf(stderr, "[b200]     stall %8.3f ms  %s (%zu)\n", ms, what, arg);
+    }
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     void ensure(size_t bytes)
     {
         if (bytes <= cap) return;
+        TraceStall ts("device buffer growth, bytes", bytes);
         if (p) CK(cudaFree(p));
         p = nullptr;
         cap = 0;
@@ -180,6 +200,7 @@ extern int g_tune_g2blocks;  // k_accumulate<Fq2> builds: 1 (default) ptxas may 
 extern int g_tune_red_block;  // threads per block of k_reduce_segments (32, 64, 96 or 128)
 extern int g_tune_g1paired;  // k_accumulate<Fq> with the mixed addition's independent products issued in pairs: 1 (ptxas picks the registers), 2 (four blocks per SM)
 extern int g_tune_quads;  // 1 (default): stage 2 of the window reduction with quad-cooperative additions (k_reduce_bits_quad); 0: one thread per partial sum
+extern int g_tune_dense_direct;  // 1 (default): in pipelined MSMs k_accumulate writes single-task buckets straight into the dense array; 0: every chunk folds all buckets
 extern int g_tune_g2pair;  // 1: G2 accumulation with two lanes per task (measured 5 % slower: profiles/r2n_g2_lane_pairs.jsonl); 0 (default): one thread per task
 extern int g_tune_even_chunks;  // 1 (default): equal upload chunks; 0: short first chunk (measured: no gain)
 extern int g_tune_ba;    // batch-affine tree levels in front of the XYZZ accumulation: 0 (off), 1 or 2
@@ -195,6 +216,7 @@ inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 
 #define LAUNCH(D, kernel, grid, block, smem, st, ...)             \
     do {                                                          \
+        TraceStall ts_("launch of " #kernel, 0);                  \
         kernel<<<grid, block, smem, st>>>(__VA_ARGS__);           \
         (D).launches++;                                           \
         CK(cudaGetLastError());                                   \

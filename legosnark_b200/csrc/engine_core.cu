@@ -16,7 +16,7 @@ namespace eng {
 std::mutex g_mu;
 std::string g_err;
 // B200_TRACE=1: one stderr line per C-ABI call (ApiScope below) and per phase of b200_init
-static const bool g_trace = [] { const char *e = std::getenv("B200_TRACE"); return e && *e && *e != '0'; }();
+bool g_trace = [] { const char *e = std::getenv("B200_TRACE"); return e && *e && *e != '0'; }();
 static double trace_ms()
 {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -40,7 +40,7 @@ std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1, g_tune_host_horner = 1;
-int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 0, g_tune_even_chunks = 1, g_tune_g2blocks = 1, g_tune_red_block = 128, g_tune_g1paired = 0, g_tune_quads = 1;
+int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 0, g_tune_even_chunks = 1, g_tune_g2blocks = 1, g_tune_red_block = 128, g_tune_g1paired = 0, g_tune_quads = 1, g_tune_dense_direct = 1;
 bool g_scalars_resident = false;
 
 static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal
@@ -189,6 +189,7 @@ static int apply_tuning(const std::string &k, int value)
     else if (k == "reduce_marginals") g_tune_marginals = value;  // 0: bit decomposition over all segments (round 1)
     else if (k == "batch_affine") g_tune_ba = std::min(std::max(value, 0), 2);  // tree levels of affine pair additions before the XYZZ tail
     else if (k == "reduce_block") g_tune_red_block = value;  // threads per block of k_reduce_segments
+    else if (k == "dense_direct") g_tune_dense_direct = value;  // 0: pipelined MSMs fold every bucket after every chunk
     else if (k == "reduce_quads") g_tune_quads = value;       // 0: one thread per partial sum in stage 2 of the window reduction (k_reduce_bits)
     else if (k == "g1_paired") g_tune_g1paired = value;      // 1 / 2: paired products in k_accumulate<Fq> (2: compiled for four blocks per SM)
     else if (k == "g2_blocks") g_tune_g2blocks = value;      // 3: the 168-register build of k_accumulate<Fq2> (three blocks per SM)

@@ -285,8 +285,10 @@ inline void launch_accumulate_g2pair(Device &, cudaStream_t, const Affine<Fq> *,
 
 // bucket sort of the digits of `n` scalars and accumulation of the bucket (task) sums into D.partial
 template <class F>
-void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const Affine<F> *d_aff, const uint8_t *d_flags,
-                             const Fr *d_scalars, size_t n, bool first_chunk = true, bool seeded = false)
+// dense_direct (pipelined MSMs): k_accumulate writes single-task buckets straight into D.bucket_sum; returns whether it did
+// (the optional accumulation kernels do not, the caller then folds every bucket)
+bool enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const Affine<F> *d_aff, const uint8_t *d_flags,
+                             const Fr *d_scalars, size_t n, bool first_chunk = true, bool seeded = false, bool dense_direct = false)
 {
     const MsmGeom &g = P.g;
     SortGeom sg;
@@ -324,6 +326,8 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
     }
     const uint32_t *tbk = D.task_bucket.as<uint32_t>();
     const XYZZ<F> *seed = seeded ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr;  // chunk > 0 of a pipelined MSM
+    XYZZ<F> *dout = dense_direct ? D.bucket_sum.as<XYZZ<F>>() : (XYZZ<F> *)nullptr;
+    bool wrote_dense = dense_direct;
     CK(cudaEventRecord(D.ev[2], st));
     if (part_sort && ba) {
         // levels of independent affine pair additions with shared inversions, then the XYZZ tail (pair_kernels.cuh)
@@ -342,23 +346,25 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
         }
         LAUNCH(D, (k_accumulate_pa<F>), cdiv(max_tasks, 128), 128, 0, st, last, ba, (const uint2 *)meta, (const uint32_t *)order,
                (const uint32_t *)totals, partial, tbk, seed);
+        wrote_dense = false;
     } else if (sizeof(F) == 64 && g_tune_g2pair) {
         launch_accumulate_g2pair(D, st, d_aff, entries, meta, order, totals, partial, tbk, seed, max_tasks);
+        wrote_dense = false;
     } else if (sizeof(F) == 32 && g_tune_g1paired) {  // independent products of the mixed addition issued in pairs
         if (g_tune_g1paired == 2)
             LAUNCH(D, (k_accumulate<F, (sizeof(F) == 32 ? 4 : 0), sizeof(F) == 32>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order,
-                   totals, partial, tbk, seed);
+                   totals, partial, tbk, seed, dout);
         else
             LAUNCH(D, (k_accumulate<F, 0, sizeof(F) == 32>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk,
-                   seed);
+                   seed, dout);
     } else if (sizeof(F) == 64 && g_tune_g2blocks == 1) {  // ptxas free to use 255 registers (252 used), two blocks per SM
         LAUNCH(D, (k_accumulate<F, (sizeof(F) == 64 ? 1 : 0)>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial,
-               tbk, seed);
+               tbk, seed, dout);
     } else if (sizeof(F) == 64 && g_tune_g2blocks == 3) {
         LAUNCH(D, (k_accumulate<F, (sizeof(F) == 64 ? 3 : 0)>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial,
-               tbk, seed);
+               tbk, seed, dout);
     } else {
-        LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk, seed);
+        LAUNCH(D, (k_accumulate<F>), cdiv(max_tasks, 128), 128, 0, st, d_aff, entries, meta, order, totals, partial, tbk, seed, dout);
     }
     CK(cudaEventRecord(D.ev[3], st));
     LAUNCH(D, (k_bucket_combine<F>), (uint32_t)D.sms * 8, 128, 0, st, cnt, toff, split, totals, g, partial);
@@ -374,13 +380,21 @@ void enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
         LAUNCH(D, (k_sum_ones<F>), (uint32_t)D.sms * 2, ONES_THREADS, 0, st, d_aff + (g.pre_stride ? g.pre_off : 0),
                (const uint32_t *)D.ones_idx.as<uint32_t>(), (const uint32_t *)(totals + 3), D.ones_part.as<XYZZ<F>>(),
                D.ones_done.as<uint32_t>(), first_chunk, D.ones_sum.as<XYZZ<F>>());
+    return wrote_dense;
 }
 
+// direct: k_accumulate already wrote every single-task bucket into the dense array (which was cleared before the first
+// chunk); only the buckets that were split into several tasks are copied
 template <class F>
-void enqueue_fold(Device &D, cudaStream_t st, const MsmPlan &P, bool first)
+void enqueue_fold(Device &D, cudaStream_t st, const MsmPlan &P, bool first, bool direct)
 {
-    LAUNCH(D, (k_bucket_fold<F>), cdiv(P.g.NB, 128), 128, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(), D.partial.as<XYZZ<F>>(),
-           P.g.NB, first, !first, D.bucket_sum.as<XYZZ<F>>());
+    if (direct)
+        LAUNCH(D, (k_bucket_fold_lists<F>), (uint32_t)D.sms * 4, 128, 0, st, (const uint32_t *)D.toff.as<uint32_t>(),
+               (const XYZZ<F> *)D.partial.as<XYZZ<F>>(), (const uint32_t *)D.split.as<uint32_t>(), (const uint32_t *)D.big.as<uint32_t>(),
+               (const uint32_t *)D.totals.as<uint32_t>(), D.bucket_sum.as<XYZZ<F>>());
+    else
+        LAUNCH(D, (k_bucket_fold<F>), cdiv(P.g.NB, 128), 128, 0, st, D.cnt.as<uint32_t>(), D.toff.as<uint32_t>(), D.partial.as<XYZZ<F>>(),
+               P.g.NB, first, !first, D.bucket_sum.as<XYZZ<F>>());
 }
 
 // window reduction + D2H of the W window sums (and the entry / task totals of the last sort)
@@ -479,15 +493,20 @@ MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *
     // order the copy stream after whatever the compute stream still has in flight on these buffers
     CK(cudaEventRecord(D.ev_sync, st));
     CK(cudaStreamWaitEvent(D.copy_stream, D.ev_sync, 0));
+    // the dense per-bucket sums: k_accumulate writes whole buckets into it directly (knob dense_direct), so it starts out as
+    // all infinity (= all zero bytes) instead of being initialised by the first fold
+    const bool want_direct = g_tune_dense_direct != 0;
+    if (want_direct) CK(cudaMemsetAsync(D.bucket_sum.p, 0, (size_t)P.g.NB * sizeof(XYZZ<F>), st));
     for (size_t j = 0; j < ranges.size(); j++) {
         const size_t lo = ranges[j].first, cnt = ranges[j].second;
         upload(D.copy_stream, lo, cnt);
         CK(cudaEventRecord(D.ev_ready[j], D.copy_stream));
         CK(cudaStreamWaitEvent(st, D.ev_ready[j], 0));
         run_ingest<F, false>(D, st, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
-        enqueue_sort_accumulate<F>(D, st, P, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, D.scalars.as<Fr>() + lo,
-                                   cnt, j == 0, j > 0);
-        enqueue_fold<F>(D, st, P, j == 0);
+        // with the array cleared, chunk 0 can be "seeded" like the others (it reads infinity)
+        const bool direct = enqueue_sort_accumulate<F>(D, st, P, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo,
+                                                       D.scalars.as<Fr>() + lo, cnt, j == 0, j > 0 || want_direct, want_direct);
+        enqueue_fold<F>(D, st, P, j == 0 && !want_direct, direct);
     }
     enqueue_reduce<F>(D, st, P, true);
     CK(cudaEventRecord(D.ev[1], st));

@@ -449,7 +449,7 @@ static __global__ void __launch_bounds__(256) k_task_meta(const uint32_t *__rest
         const uint32_t rem = cnt[b] - j * g.L;
         const uint32_t len = rem < g.L ? rem : g.L;
         meta[t] = make_uint2(off[b] + j * g.L, len);
-        task_bucket[t] = b | (j == 0 ? 0x80000000u : 0u);
+        task_bucket[t] = b | (j == 0 ? 0x80000000u : 0u) | (cnt[b] <= g.L ? 0x40000000u : 0u);  // bit 31: first task; bit 30: only task
         atomicAdd(&sh_hist[len], 1u);
         if (j == 0 && cnt[b] > g.L) {  // bucket spans several tasks
             if (tasks_of(cnt[b], g.L) > BIG_TASKS) big[atomicAdd(&totals[4], 1u)] = b;
@@ -522,7 +522,8 @@ template <class F, int MINB = 0, bool PAIRED = false>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
                                                      const uint2 *__restrict__ meta, const uint32_t *__restrict__ order,
                                                      const uint32_t *__restrict__ totals, XYZZ<F> *__restrict__ partial,
-                                                     const uint32_t *__restrict__ task_bucket, const XYZZ<F> *__restrict__ seed)
+                                                     const uint32_t *__restrict__ task_bucket, const XYZZ<F> *seed,
+                                                     XYZZ<F> *dense_out)
 {
     const uint32_t ntasks = totals[1];
     const uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -531,9 +532,9 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__res
     const uint2 m = meta[t];
     const uint32_t *e = entries + m.x;
     XYZZ<F> acc = XYZZ<F>::inf();
+    const uint32_t tb = (seed || dense_out) ? task_bucket[t] : 0u;
     if (seed) {  // later chunks of a pipelined MSM: the first task of a bucket continues from the bucket's sum so far
-        const uint32_t tb = task_bucket[t];
-        if (tb >> 31) acc = seed[tb & 0x7fffffffu];
+        if (tb >> 31) acc = seed[tb & 0x3fffffffu];
     }
     if (sizeof(F) <= 32) {
         // G1: the next point is loaded into registers while this one is added
@@ -564,7 +565,11 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__res
             xyzz_madd(acc, q.x, q.y, neg != 0);
         }
     }
-    partial[t] = acc;
+    // pipelined MSMs: a bucket that is ONE task writes its new total straight into the dense per-bucket array that lives across
+    // the chunks (seed and dense_out are the same array; only this thread touches the bucket), so the fold pass only has to
+    // copy the buckets that were split into several tasks
+    if (dense_out && (tb & 0x40000000u)) dense_out[tb & 0x3fffffffu] = acc;
+    else partial[t] = acc;
 }
 
 // ------------------------------------------------------------------------------
@@ -935,6 +940,20 @@ __global__ void __launch_bounds__(128) k_bucket_fold(const uint32_t *__restrict_
         XYZZ<F> acc = dense[b];
         xyzz_add_cold(&acc, &q);
         dense[b] = acc;
+    }
+}
+
+// the same for the buckets that were split into several tasks only (lists of k_task_meta / k_task_emit: `split`, totals[2]
+// entries; `big`, totals[4]); every other non-empty bucket was written into `dense` by k_accumulate itself
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_fold_lists(const uint32_t *__restrict__ toff, const XYZZ<F> *__restrict__ partial,
+                                                            const uint32_t *__restrict__ split, const uint32_t *__restrict__ big,
+                                                            const uint32_t *__restrict__ totals, XYZZ<F> *__restrict__ dense)
+{
+    const uint32_t ns = totals[2], nb = totals[4];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ns + nb; i += gridDim.x * blockDim.x) {
+        const uint32_t b = i < ns ? split[i] : big[i - ns];
+        dense[b] = partial[toff[b]];
     }
 }
 

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) k_accumulate_pa(const Affine<F> *__restri
     XYZZ<F> acc = XYZZ<F>::inf();
     if (seed) {
         const uint32_t tb = task_bucket[t];
-        if (tb >> 31) acc = seed[tb & 0x7fffffffu];
+        if (tb >> 31) acc = seed[tb & 0x3fffffffu];
     }
     if (sizeof(F) <= 32) {  // G1: next point in registers during the addition; G2: no room (see k_accumulate)
         Affine<F> p = src[0];

@@ -385,7 +385,7 @@ static __global__ void __launch_bounds__(FINE_THREADS) k_task_emit(const uint32_
         const uint32_t rem = cs[b] - j * L;
         const uint32_t len = rem < L ? rem : L;
         meta[t0 + t] = make_uint2(os[b] + j * L, len);
-        task_bucket[t0 + t] = (b0 + b) | (j == 0 ? 0x80000000u : 0u);
+        task_bucket[t0 + t] = (b0 + b) | (j == 0 ? 0x80000000u : 0u) | (cs[b] <= L ? 0x40000000u : 0u);  // bit 31: first task; bit 30: only task
         order[lstart[len] + atomicAdd(&lh[len], 1u)] = t0 + t;
     }
 }

@@ -45,16 +45,21 @@ def test_pipelined_upload_chunks(engine, orc, golden, grp):
     s = inputs.fr_uniform(orc, n, seed=42)
     want = orc.msm(grp, P, s)
     try:
-        for chunks, c, L in ((2, 0, 0), (3, 7, 4), (4, 10, 0), (7, 4, 2), (16, 12, 0)):
-            engine.set_tuning(c, L)
-            engine.set_pipeline_chunks(chunks)
-            assert (engine.multi_exp(grp, P, s) == want).all(), (grp, chunks, c, L)
-            if c == 0:
-                continue  # fixtures are small: they take the single-kernel path unless the geometry is forced
-            for name in g["names"]:
-                B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
-                assert (engine.multi_exp(grp, B, S) == R).all(), (grp, name, chunks, c, L)
+        # dense_direct = 1 (default): whole buckets go from k_accumulate straight into the array that lives across the chunks and
+        # only split buckets are folded; 0: every chunk folds every bucket
+        for dense_direct in (1, 0):
+            engine.set_tuning_ex("dense_direct", dense_direct)
+            for chunks, c, L in ((2, 0, 0), (3, 7, 4), (4, 10, 0), (7, 4, 2), (16, 12, 0)):
+                engine.set_tuning(c, L)
+                engine.set_pipeline_chunks(chunks)
+                assert (engine.multi_exp(grp, P, s) == want).all(), (grp, chunks, c, L, dense_direct)
+                if c == 0:
+                    continue  # fixtures are small: they take the single-kernel path unless the geometry is forced
+                for name in g["names"]:
+                    B, S, R = g[f"{name}__bases"], g[f"{name}__scalars"], g[f"{name}__result"]
+                    assert (engine.multi_exp(grp, B, S) == R).all(), (grp, name, chunks, c, L, dense_direct)
     finally:
+        engine.set_tuning_ex("dense_direct", 1)
         engine.set_tuning(0, 0)
         engine.set_pipeline_chunks(0)
 

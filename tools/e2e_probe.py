@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
-"""tools/e2e_probe.py — the host-buffer call b200_msm_g1 (pinned Jacobian bases + scalars, the bench's `e2e`) under forced
-window sizes and upload-chunk counts: is the pipelined plain-key path at its best geometry?  One JSON line per setting."""
-import json, os, sys, time
+"""tools/e2e_probe.py — the host-buffer call b200_msm_g1 / g2 (pinned Jacobian bases + scalars: the bench's `e2e`) for a grid of
+tuning knobs, window sizes and upload-chunk counts.  One JSON line per setting; every result is compared with the first.
+
+    python tools/e2e_probe.py [log2n = 20] [--group g1] [--knobs dense_direct=1,0 window_bits=0,15 chunks=0,3]"""
+import argparse, itertools, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,32 +11,46 @@ import torch
 import legosnark_b200 as lb
 from bench import generator, random_scalars
 
-log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-n = 1 << log2n
+ap = argparse.ArgumentParser()
+ap.add_argument("log2n", nargs="?", type=int, default=20)
+ap.add_argument("--group", default="g1")
+ap.add_argument("--knobs", nargs="*", default=[])
+a = ap.parse_args()
+n = 1 << a.log2n
 lb.init(1)
 k = random_scalars(n, 2)
-P = torch.from_numpy(lb.batch_exp_once("g1", generator("g1"), k).view(np.int64)).pin_memory().numpy().view(np.uint64)
+P = torch.from_numpy(lb.batch_exp_once(a.group, generator(a.group), k).view(np.int64)).pin_memory().numpy().view(np.uint64)
 s = torch.from_numpy(random_scalars(n, 1).view(np.int64)).pin_memory().numpy().view(np.uint64)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+names, grids = [], []
+for kv in a.knobs:
+    name, vals = kv.split("=")
+    names.append(name)
+    grids.append([int(v) for v in vals.split(",")])
 ref = None
-for even in (1, 0):
-  lb.set_tuning_ex("even_chunks", even)
-  for chunks in ((0, 3, 4, 5, 6, 8) if not even else (0,)):
-    for c in (0,):
-        lb.set_tuning(c, 0)
-        lb.set_pipeline_chunks(chunks)
-        ts = []
-        for it in range(8):
-            flush.zero_()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            r = lb.multi_exp("g1", P, s)
-            ts.append((time.perf_counter() - t0) * 1e3)
-        if ref is None:
-            ref = r
-        st = lb.last_stats()
-        print(json.dumps({"log2n": log2n, "even_chunks": even, "chunks": chunks, "c_forced": c, "c": st["window_bits"], "W": st["num_windows"],
-                          "e2e_ms_median": float(np.median(ts[2:])), "e2e_ms_min": float(np.min(ts[2:])), "same": bool((r == ref).all())}), flush=True)
+for combo in itertools.product(*grids) if grids else [()]:
+    for name, v in zip(names, combo):
+        if name == "window_bits":
+            lb.set_tuning(v, 0)
+        elif name == "chunks":
+            lb.set_pipeline_chunks(v)
+        else:
+            lb.set_tuning_ex(name, v)
+    ts, dev = [], []
+    for it in range(10):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = lb.multi_exp(a.group, P, s)
+        ts.append((time.perf_counter() - t0) * 1e3)
+        dev.append(lb.last_stats()["device_ms"])
+    if ref is None:
+        ref = r
+    st = lb.last_stats()
+    print(json.dumps({"group": a.group, "log2n": a.log2n, "knobs": dict(zip(names, combo)), "c": st["window_bits"], "W": st["num_windows"],
+                      "e2e_ms_median": float(np.median(ts[2:])), "e2e_ms_min": float(np.min(ts[2:])),
+                      "device_ms_median": float(np.median(dev[2:])), "launches": st["kernel_launches"], "same": bool((r == ref).all())}),
+          flush=True)
 lb.set_tuning(0, 0)
 lb.set_pipeline_chunks(0)
 lb.shutdown()
