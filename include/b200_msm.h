@@ -301,11 +301,18 @@ int b200_set_tuning(int window_bits, int chunk_len);
 /* More knobs for sweeps: "reduce_log_segment" (-1 = model), "reduce_split" (0 = auto),
  * "host_horner" (0: a precomputed key's one-window reduction is weighted and summed on the device too),
  * "ones_filter" (0: scalars equal to one go through the bucket sort instead of the direct sum),
- * "use_precomputed" (0: ignore a key's precomputed levels; 1: where the cost model prefers them; 2: always). */
+ * "use_precomputed" (0: ignore a key's precomputed levels; 1: where the cost model prefers them; 2: always).
+ * Measured alternatives that stay in the tree (defaults first): "partition_sort" (1 / 0: round-1 global-atomics counting sort),
+ * "reduce_quads" (1 / 0: one thread per partial sum in stage 2 of the window reduction), "reduce_marginals" (0 / 1),
+ * "reduce_block" (128 / 32..96 threads per block in stage 1), "dense_direct" (1 / 0: pipelined MSMs fold every bucket after
+ * every chunk), "batch_affine" (0 / 1, 2 tree levels of affine pair additions), "g2_lane_pairs" (0 / 1), "g2_blocks" (1 / 2, 3:
+ * register budgets of the G2 accumulation), "g1_paired" (0 / 1), "even_chunks" (1 / 0).  DESIGN.md section 4 has the numbers.
+ * The same keys can be set for a whole process with B200_TUNE="key=value,key=value"; B200_TRACE=1 prints one stderr line per
+ * call (wall time, sizes, transfers) and every host stall above 1 ms inside it. */
 int b200_set_tuning_ex(const char *key, int value);
 /* Host-buffer MSMs (b200_msm_g1/g2) upload their inputs in `chunks` index chunks whose H2D copy
  * overlaps the sort + accumulation of the previous chunk (0 = auto: 1 below 2^17 points, 2 below
- * 2^19, else 4; at most 16).  1 disables the pipeline. */
+ * 2^19, 4 below 2^22, else 8; at most 16).  1 disables the pipeline. */
 int b200_set_pipeline_chunks(int chunks);
 /* IMAD roofline microbenchmark on every SM of device 0; returns multiply-adds (lane-ops)
  * per second.  kind 0: the 32x32+64 multiply-add stream of the Montgomery product
