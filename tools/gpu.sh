@@ -12,6 +12,7 @@
 #   launches[:args]       ncu launch list (gpu__time_duration) of python bench.py --steps 2 --warmup 3 --no-cpu-baseline <args>
 #   ncufull:<regex>[+args] ncu --set full of the kernels matching <regex> in the same command; also writes the raw/details CSV pages
 #   integ:<binary>+<args> integration/_ref/<binary> <args>
+#   sanitize:<tool>+<pytest args>  compute-sanitizer --tool <memcheck|racecheck|synccheck> over python -m pytest -m gpu <args>
 #   mgpu:<N>[+args]       torchrun with N ranks on one node: python bench.py --gpus N <args> (needs gpurun --gpus N)
 set -u
 TAG=$1; shift
@@ -37,6 +38,8 @@ for step in "$@"; do
              ncu -i ${O}_ncu_$short.ncu-rep --page raw --csv > ${O}_ncu_${short}_raw.csv 2>/dev/null
              ncu -i ${O}_ncu_$short.ncu-rep --page details --csv > ${O}_ncu_${short}_details.csv 2>/dev/null ;;
     integ)   ( time B200_GPUS=1 timeout 1500 integration/_ref/"${A[0]}" "${A[@]:1}" ) 2>&1 | grep -E '^\{|^\[b200\]|leave|real|rror|terminate|what|fault' >> ${O}_integration.log ;;
+    sanitize) tool=${A[0]}
+             ( timeout 2400 compute-sanitizer --tool $tool --print-limit 20 python -m pytest -m gpu -x -q "${A[@]:1}" 2>&1 | tail -25; echo "exit $?" ) > ${O}_compute_sanitizer_$tool.log ;;
     mgpu)    N=${A[0]}
              timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
                bench.py --gpus $N "${A[@]:1}" >> ${O}_bench_n$N.jsonl 2>> ${O}_bench_n$N.err ;;
