@@ -392,6 +392,38 @@ def test_alternative_kernels_under_their_knobs(engine, orc, golden, grp):
         pre.close()
 
 
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_reduction_meets_equal_and_opposite_sums(engine, orc, grp):
+    """The adders of the window reduction must take the doubling and the cancellation branch too: with one base repeated and
+    the scalars 2 and 6 (buckets 1 and 5: the same position in two neighbouring segments of four buckets) the two segment sums
+    are the SAME point, so stage 2 adds a point to itself -- inside the quad-cooperative adder (default) and the serial one;
+    with -P on the second half they are opposite points and the sum is the point at infinity on the way."""
+    n = 6000
+    P, _ = inputs.bases(orc, grp, 1, seed=871, affine=False)
+    B = np.tile(P[0], (n, 1))
+    s = np.tile(ints_to_mont([2], R_ORDER), (n, 1))
+    s[n // 2:] = ints_to_mont([6], R_ORDER)
+    Bneg = B.copy()
+    Bneg[n // 2:] = inputs.negate(orc, grp, P[0:1])[0]
+    s_eq = np.tile(ints_to_mont([2], R_ORDER), (n, 1))  # P and -P in the same bucket position of the same segment sums to zero
+    want = orc.msm(grp, B, s, chunks=orc.max_threads(), variant=1)
+    want_neg = orc.msm(grp, Bneg, s, chunks=orc.max_threads(), variant=1)
+    want_zero = orc.msm(grp, Bneg, s_eq, chunks=orc.max_threads(), variant=1)
+    try:
+        for quads in (1, 0):
+            engine.set_tuning_ex("reduce_quads", quads)
+            for c, logS in ((8, 2), (8, 0), (6, 1), (10, 2)):
+                engine.set_tuning(c, 0)
+                engine.set_tuning_ex("reduce_log_segment", logS)
+                assert (engine.multi_exp(grp, B, s) == want).all(), (quads, c, logS, "equal sums")
+                assert (engine.multi_exp(grp, Bneg, s) == want_neg).all(), (quads, c, logS, "opposite sums")
+                assert (engine.multi_exp(grp, Bneg, s_eq) == want_zero).all(), (quads, c, logS, "cancellation")
+    finally:
+        engine.set_tuning_ex("reduce_quads", 1)
+        engine.set_tuning_ex("reduce_log_segment", -1)
+        engine.set_tuning(0, 0)
+
+
 def _device_bases(engine, orc, grp, k):
     """P_i = k_i G made by the GPU fixed-base path, spot-checked against the oracle."""
     n = len(k)

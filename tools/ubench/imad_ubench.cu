@@ -1,6 +1,6 @@
 // imad_ubench.cu — integer-pipe microbenchmarks that decide how the Montgomery
 // multiplication is written (DESIGN.md "IMAD roofline").  Standalone: built by
-// tools/ubench/build.sh, run on the GPU box, prints one JSON line per variant.
+// tools/ubench/Makefile, run on the GPU box, prints one JSON line per variant.
 //
 // Each variant runs `iters` rounds of a fixed instruction pattern in every thread,
 // 8 CTAs x 256 threads per SM (full occupancy), and reports warp-instructions per
