@@ -35,6 +35,16 @@ inline int copy_threads()
     return n;
 }
 constexpr size_t COPY_MIN_STAGED = 8u << 20;
+// bytes per staged piece: B200_COPY_CHUNK_KB (64 .. 4096, default 4096 = the size of the pinned buffers)
+inline size_t copy_chunk()
+{
+    static const size_t n = [] {
+        const char *e = std::getenv("B200_COPY_CHUNK_KB");
+        const long v = e ? std::atol(e) : 4096;
+        return (size_t)std::max(64L, std::min(v, 4096L)) << 10;
+    }();
+    return n;
+}
 
 struct Stager {
     void *pin[COPY_THREADS_MAX][2] = {};
@@ -153,7 +163,8 @@ inline void staged_copy(Device &D, void *dst, const void *src, size_t bytes, cud
     S.init();
     // the private streams start after whatever `st` still has in flight on these buffers
     CK(cudaEventRecord(S.gate, st));
-    const size_t nchunks = (bytes + COPY_CHUNK - 1) / COPY_CHUNK;
+    const size_t CHUNK = copy_chunk();
+    const size_t nchunks = (bytes + CHUNK - 1) / CHUNK;
     const int COPY_THREADS = copy_threads();
     std::vector<std::string> errs(COPY_THREADS);
     const int dev_id = D.id;
@@ -164,7 +175,7 @@ inline void staged_copy(Device &D, void *dst, const void *src, size_t bytes, cud
                 int b = 0;
                 size_t pending_off[2] = {0, 0}, pending_len[2] = {0, 0};
                 for (size_t c = (size_t)t; c < nchunks; c += COPY_THREADS, b ^= 1) {
-                    const size_t off = c * COPY_CHUNK, len = std::min(COPY_CHUNK, bytes - off);
+                    const size_t off = c * CHUNK, len = std::min(CHUNK, bytes - off);
                     if (ToDevice) {
                         CK(cudaEventSynchronize(S.ev[t][b]));  // the DMA that last read this pinned buffer is done
                         memcpy(S.pin[t][b], (const char *)src + off, len);

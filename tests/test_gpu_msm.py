@@ -47,8 +47,9 @@ def test_pipelined_upload_chunks(engine, orc, golden, grp):
     try:
         # dense_direct = 1 (default): whole buckets go from k_accumulate straight into the array that lives across the chunks and
         # only split buckets are folded; 0: every chunk folds every bucket
-        for dense_direct in (1, 0):
+        for dense_direct, part_sort in ((1, 1), (0, 1), (1, 0)):  # (1, 0): the round-1 counting sort feeds the same lists
             engine.set_tuning_ex("dense_direct", dense_direct)
+            engine.set_tuning_ex("partition_sort", part_sort)
             for chunks, c, L in ((2, 0, 0), (3, 7, 4), (4, 10, 0), (7, 4, 2), (16, 12, 0)):
                 engine.set_tuning(c, L)
                 engine.set_pipeline_chunks(chunks)
@@ -60,6 +61,7 @@ def test_pipelined_upload_chunks(engine, orc, golden, grp):
                     assert (engine.multi_exp(grp, B, S) == R).all(), (grp, name, chunks, c, L, dense_direct)
     finally:
         engine.set_tuning_ex("dense_direct", 1)
+        engine.set_tuning_ex("partition_sort", 1)
         engine.set_tuning(0, 0)
         engine.set_pipeline_chunks(0)
 

@@ -23,5 +23,6 @@ for it in range(10):
     r = lb.multi_exp("g1", P, s)
     ts.append((time.perf_counter() - t0) * 1e3)
 print(json.dumps({"log2n": log2n, "copy_threads": os.environ.get("B200_COPY_THREADS", "default(4)"),
+                  "copy_chunk_kb": os.environ.get("B200_COPY_CHUNK_KB", "default(4096)"),
                   "e2e_pageable_ms_median": float(np.median(ts[3:])), "min": float(np.min(ts[3:]))}), flush=True)
 lb.shutdown()
