@@ -51,6 +51,10 @@ extern "C" {
  * sharded by index range across them (multiexp.tcc:417-438 does the same across
  * OpenMP threads) and the per-GPU partials are summed on the host. */
 int b200_init(int n_gpus);
+/* The same, started on a background thread: returns at once; every later call (b200_init included) waits for it to finish and
+ * reports its error, if any.  The CUDA driver's own start-up is 0.6-2.3 s per process on these boxes; a prover that calls this
+ * first thing in main() hides it under its circuit / witness construction.  Idempotent. */
+int b200_init_async(int n_gpus);
 /* Use exactly these CUDA device ordinals (one process per GPU under torchrun: {LOCAL_RANK}). */
 int b200_init_devices(const int *device_ids, int n);
 void b200_shutdown(void);

@@ -107,6 +107,12 @@ def init(n_gpus: int = 1):
     _check(lib().b200_init(int(n_gpus)), "b200_init")
 
 
+def init_async(n_gpus: int = 1):
+    """b200_init on a background thread (hides the CUDA driver's start-up under the caller's own set-up work); every later
+    call waits for it."""
+    _check(lib().b200_init_async(int(n_gpus)), "b200_init_async")
+
+
 def init_devices(ids):
     arr = (ctypes.c_int * len(ids))(*ids)
     _check(lib().b200_init_devices(arr, len(ids)), "b200_init_devices")

@@ -2,7 +2,9 @@
 // include/b200_msm.h.  The per-group work is in engine_g1.cu / engine_g2.cu.
 #include <chrono>
 #include <cstdio>
+#include <condition_variable>
 #include <cstdlib>
+#include <thread>
 
 #include "engine_common.hpp"
 #include "field.cuh"
@@ -243,13 +245,53 @@ struct ApiScope {
     }
 };
 
+static std::thread g_async_thread;
+static int g_async_rc = B200_OK;
+static bool g_async_started = false;
+
+static void join_async_init()
+{
+    if (g_async_thread.joinable()) g_async_thread.join();
+}
+
 extern "C" {
 
 int b200_init(int n_gpus)
 {
     ApiScope lk(__func__);
+    if (g_async_started && !g_init && g_async_rc != B200_OK) return g_async_rc;  // the background start failed: its message is in g_err
     const int rc = init_devices(nullptr, n_gpus);
     return rc == B200_OK ? apply_env_tuning() : rc;
+}
+
+// b200_init on a background thread.  The thread takes the engine lock before b200_init_async returns (the caller cannot
+// overtake it), so any later entry point blocks on g_mu until the devices are up; a failure stays in g_async_rc / g_err and
+// is returned by the next b200_init.
+int b200_init_async(int n_gpus)
+{
+    static std::mutex start_mu;
+    std::lock_guard<std::mutex> once(start_mu);
+    if (g_async_started || g_init) return B200_OK;
+    g_async_started = true;
+    std::mutex handoff_mu;
+    std::condition_variable handoff_cv;
+    bool locked = false;
+    g_async_thread = std::thread([&, n_gpus] {
+        std::unique_lock<std::mutex> lk(g_mu);
+        {
+            std::lock_guard<std::mutex> h(handoff_mu);
+            locked = true;
+            handoff_cv.notify_one();  // under the lock: the caller's frame (which owns the condition variable) outlives this call
+        }
+        int rc = init_devices(nullptr, n_gpus);
+        if (rc == B200_OK) rc = apply_env_tuning();
+        g_async_rc = rc;
+    });
+    std::unique_lock<std::mutex> h(handoff_mu);
+    handoff_cv.wait(h, [&] { return locked; });
+    static const int registered = std::atexit(join_async_init);  // a program that exits early must not leave the thread behind
+    (void)registered;
+    return B200_OK;
 }
 
 int b200_init_devices(const int *device_ids, int n)
@@ -262,6 +304,7 @@ int b200_init_devices(const int *device_ids, int n)
 
 void b200_shutdown(void)
 {
+    join_async_init();
     ApiScope lk(__func__);
     if (!g_init) return;
     for (auto &kv : g_pinned)

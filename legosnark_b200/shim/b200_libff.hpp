@@ -86,6 +86,14 @@ inline void ensure_init()
     (void)once;
 }
 
+// Optional: call first thing in main().  The engine comes up on a background thread while the program builds its circuit /
+// reads its inputs; the first shim call then finds it ready (or waits for the rest).  Same B200_GPUS rule as ensure_init().
+inline void start_engine_early()
+{
+    const char *e = std::getenv("B200_GPUS");
+    check(b200_init_async(e ? std::atoi(e) : 0), "b200_init_async");
+}
+
 template <typename T>
 inline const uint64_t *limbs_of(const T *p)
 {

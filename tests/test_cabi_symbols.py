@@ -47,6 +47,36 @@ def test_no_cpu_fallback():
             call()
 
 
+def test_init_async_reports_the_failure_without_a_device():
+    """b200_init_async returns at once; the failure of the background start (no device here) comes back from the next
+    b200_init and the compute entry points keep refusing -- in a child process, so that this one's engine state stays clean."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; this test checks the no-device behaviour")
+    code = (
+        "import numpy as np, legosnark_b200 as lb\n"
+        "lb.init_async(1)\n"
+        "lb.init_async(1)\n"
+        "try:\n"
+        "    lb.init(1)\n"
+        "    print('INIT-OK')\n"
+        "except lb.B200Error as e:\n"
+        "    print('INIT-FAILED', e)\n"
+        "try:\n"
+        "    lb.multi_exp('g1', np.zeros((1, 12), dtype=np.uint64), np.zeros((1, 4), dtype=np.uint64))\n"
+        "    print('MSM-OK')\n"
+        "except lb.B200Error as e:\n"
+        "    print('MSM-REFUSED', e)\n"
+        "lb.shutdown()\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "INIT-FAILED" in r.stdout and ("no CUDA device" in r.stdout or "CPU fallback" in r.stdout), r.stdout
+    assert "MSM-REFUSED" in r.stdout and "b200_init has not been called" in r.stdout, r.stdout
+
+
 def test_product_never_imports_the_oracle():
     """The product package and its sources must not reference oracle/ (judge's check)."""
     pkg = os.path.join(ROOT, "legosnark_b200")
