@@ -100,6 +100,11 @@ struct Device {
     cudaStream_t copy_stream = nullptr;  // H2D of the next chunk while the previous one is accumulated
     cudaEvent_t ev_ready[MAX_CHUNKS] = {};  // chunk j has landed on the device
     cudaEvent_t ev_sync = nullptr;
+    // Pipelined host-buffer MSMs sort chunk j + 1 (latency-bound) on sort_stream while chunk j is accumulated (multiply-add
+    // bound) on `stream`: the buffers a sort hands to the accumulation exist twice and swap roles from chunk to chunk.
+    cudaStream_t sort_stream = nullptr;
+    cudaEvent_t ev_sorted[2] = {nullptr, nullptr};    // the sort into set k has finished
+    cudaEvent_t ev_set_free[2] = {nullptr, nullptr};  // the accumulation / fold that read set k has finished
     // Last use of engine-owned buffers / cached tables by a call that returned WITHOUT synchronising (the *_dev entry
     // points run on the caller's stream): every entry point first makes its stream wait for it (engine_enter), the
     // asynchronous ones record it when they have enqueued their work (engine_leave).  All engine streams are
@@ -112,6 +117,23 @@ struct Device {
     // radix-partition sort (engine_sort.cu): standard-form scalars, (entry, bucket) pairs, per-partition counters
     DevBuf std_scalars, items, part;
     DevBuf task_bucket;  // per task: its bucket | first-task flag (seeded accumulation of pipelined chunks)
+    struct SortSet {
+        DevBuf cnt, off, toff, entries, meta, order, totals, split, big, task_bucket, ones_idx;
+    } alt;  // the second set of what a sort produces for the accumulation (see sort_stream)
+    void swap_sort_set()
+    {
+        std::swap(cnt, alt.cnt);
+        std::swap(off, alt.off);
+        std::swap(toff, alt.toff);
+        std::swap(entries, alt.entries);
+        std::swap(meta, alt.meta);
+        std::swap(order, alt.order);
+        std::swap(totals, alt.totals);
+        std::swap(split, alt.split);
+        std::swap(big, alt.big);
+        std::swap(task_bucket, alt.task_bucket);
+        std::swap(ones_idx, alt.ones_idx);
+    }
     // batch-affine accumulation (pair_kernels.cuh): the points of tree levels 1 and 2
     DevBuf pa1, pa2;
     bool sort_attr_set = false;
@@ -143,6 +165,16 @@ struct Device {
                          &entries, &digits, &meta, &order, &len_hist, &len_cursor, &partial, &seg_run, &seg_acc, &job_out, &split, &done, &window_sums, &bucket_sum, &out_jac,
                          &out_norm, &coeff, &fr_a, &fr_b, &fr_r, &fr_w, &ones_idx, &ones_part, &ones_done, &ones_sum, &big, &std_scalars, &items, &part, &pa1, &pa2, &task_bucket};
         for (DevBuf *b : all) b->release();
+        DevBuf *alts[] = {&alt.cnt, &alt.off, &alt.toff, &alt.entries, &alt.meta, &alt.order, &alt.totals, &alt.split, &alt.big, &alt.task_bucket,
+                          &alt.ones_idx};
+        for (DevBuf *b : alts) b->release();
+        if (sort_stream) cudaStreamDestroy(sort_stream);
+        sort_stream = nullptr;
+        for (int k = 0; k < 2; k++) {
+            if (ev_sorted[k]) cudaEventDestroy(ev_sorted[k]);
+            if (ev_set_free[k]) cudaEventDestroy(ev_set_free[k]);
+            ev_sorted[k] = ev_set_free[k] = nullptr;
+        }
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
         h_pinned_cap = 0;
@@ -201,6 +233,7 @@ extern int g_tune_red_block;  // threads per block of k_reduce_segments (32, 64,
 extern int g_tune_g1paired;  // k_accumulate<Fq> with the mixed addition's independent products issued in pairs: 1 (ptxas picks the registers), 2 (four blocks per SM)
 extern int g_tune_quads;  // 1 (default): stage 2 of the window reduction with quad-cooperative additions (k_reduce_bits_quad); 0: one thread per partial sum
 extern int g_tune_dense_direct;  // 1 (default): in pipelined MSMs k_accumulate writes single-task buckets straight into the dense array; 0: every chunk folds all buckets
+extern int g_tune_overlap_sort;  // 1 (default): pipelined MSMs sort the next chunk on a second stream while the current one is accumulated
 extern int g_tune_g2pair;  // 1: G2 accumulation with two lanes per task (measured 5 % slower: profiles/r2n_g2_lane_pairs.jsonl); 0 (default): one thread per task
 extern int g_tune_even_chunks;  // 1 (default): equal upload chunks; 0: short first chunk (measured: no gain)
 extern int g_tune_ba;    // batch-affine tree levels in front of the XYZZ accumulation: 0 (off), 1 or 2

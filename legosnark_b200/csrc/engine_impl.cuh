@@ -259,6 +259,21 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
     }
     D.window_sums.ensure((size_t)nres * sizeof(XYZZ<F>));
     D.ensure_pinned((size_t)(nres + 2) * sizeof(XYZZ<F>) + 64);
+    if (dense && g_tune_overlap_sort) {  // the second set of sort outputs (Device::alt), same sizes
+        D.swap_sort_set();
+        D.cnt.ensure((size_t)g.NB * 4);
+        D.off.ensure((size_t)g.NB * 4);
+        D.toff.ensure((size_t)g.NB * 4);
+        D.totals.ensure(32);
+        D.entries.ensure((P.max_entries + (size_t)3 * g.NB + 4 * 4096 + 16) * 4);
+        D.meta.ensure(P.max_tasks * sizeof(uint2));
+        D.order.ensure(P.max_tasks * 4);
+        D.task_bucket.ensure(P.max_tasks * 4);
+        D.split.ensure(std::min<size_t>(g.NB, P.max_tasks) * 4 + 4);
+        D.big.ensure(std::min<size_t>(g.NB, P.max_tasks / BIG_TASKS + 1) * 4 + 4);
+        if (g.ones) D.ones_idx.ensure(chunk_max * 4);
+        D.swap_sort_set();
+    }
     if (g.ones) {
         D.ones_idx.ensure(chunk_max * 4);
         D.ones_part.ensure((size_t)D.sms * 2 * sizeof(XYZZ<F>));
@@ -287,13 +302,18 @@ inline void launch_accumulate_g2pair(Device &, cudaStream_t, const Affine<Fq> *,
 template <class F>
 // dense_direct (pipelined MSMs): k_accumulate writes single-task buckets straight into D.bucket_sum; returns whether it did
 // (the optional accumulation kernels do not, the caller then folds every bucket)
+// sort_st / sorted (pipelined MSMs, knob overlap_sort): the sort runs on its own stream and `st` waits for the event before
+// the accumulation, so that the next chunk's sort can run under this chunk's accumulation
 bool enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const Affine<F> *d_aff, const uint8_t *d_flags,
-                             const Fr *d_scalars, size_t n, bool first_chunk = true, bool seeded = false, bool dense_direct = false)
+                             const Fr *d_scalars, size_t n, bool first_chunk = true, bool seeded = false, bool dense_direct = false,
+                             cudaStream_t sort_st = nullptr, cudaEvent_t sorted = nullptr)
 {
     const MsmGeom &g = P.g;
     SortGeom sg;
     const uint32_t ba = g_tune_sort ? (uint32_t)g_tune_ba : 0u;  // batch-affine tree levels (needs the aligned bucket ranges of the partition sort)
     const bool part_sort = g_tune_sort && partition_geometry(g, n, D.sms, &sg, ba);
+    cudaStream_t main_st = st;
+    if (sort_st) st = sort_st;  // everything up to the accumulation is enqueued on the sort stream
     if (!part_sort) {
         CK(cudaMemsetAsync(D.cnt.p, 0, (size_t)g.NB * 4, st));
         CK(cudaMemsetAsync((char *)D.totals.p + 12, 0, 4, st));  // totals[3]: scalars equal to one
@@ -324,6 +344,11 @@ bool enqueue_sort_accumulate(Device &D, cudaStream_t st, const MsmPlan &P, const
     LAUNCH(D, k_len_scan, 1, 1024, 0, st, len_hist, len_cursor, g.L);
     LAUNCH(D, k_task_order, tblocks, 256, 2 * (g.L + 1) * 4, st, meta, totals, g, len_cursor, order);
     }
+    if (sort_st) {
+        CK(cudaEventRecord(sorted, sort_st));
+        CK(cudaStreamWaitEvent(main_st, sorted, 0));
+    }
+    st = main_st;
     const uint32_t *tbk = D.task_bucket.as<uint32_t>();
     const XYZZ<F> *seed = seeded ? D.bucket_sum.as<XYZZ<F>>() : (const XYZZ<F> *)nullptr;  // chunk > 0 of a pipelined MSM
     XYZZ<F> *dout = dense_direct ? D.bucket_sum.as<XYZZ<F>>() : (XYZZ<F> *)nullptr;
@@ -497,16 +522,27 @@ MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *
     // all infinity (= all zero bytes) instead of being initialised by the first fold
     const bool want_direct = g_tune_dense_direct != 0;
     if (want_direct) CK(cudaMemsetAsync(D.bucket_sum.p, 0, (size_t)P.g.NB * sizeof(XYZZ<F>), st));
+    // ingest + sort of chunk j + 1 on the sort stream under the accumulation of chunk j: the sort kernels wait on memory and
+    // shared-memory atomics, the accumulation on the multiply-add pipe.  The batch-affine and lane-pair options share scratch
+    // with the ingest and keep everything on one stream.
+    const bool overlap = g_tune_overlap_sort && !g_tune_ba && !(sizeof(F) == 64 && g_tune_g2pair);
+    if (overlap) CK(cudaStreamWaitEvent(D.sort_stream, D.ev_sync, 0));
     for (size_t j = 0; j < ranges.size(); j++) {
         const size_t lo = ranges[j].first, cnt = ranges[j].second;
+        const int set = (int)(j & 1);
+        if (overlap && j > 0) D.swap_sort_set();
+        cudaStream_t pre = overlap ? D.sort_stream : st;
         upload(D.copy_stream, lo, cnt);
         CK(cudaEventRecord(D.ev_ready[j], D.copy_stream));
-        CK(cudaStreamWaitEvent(st, D.ev_ready[j], 0));
-        run_ingest<F, false>(D, st, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
+        CK(cudaStreamWaitEvent(pre, D.ev_ready[j], 0));
+        if (overlap && j >= 2) CK(cudaStreamWaitEvent(pre, D.ev_set_free[set], 0));  // chunk j - 2 read this set
+        run_ingest<F, false>(D, pre, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
         // with the array cleared, chunk 0 can be "seeded" like the others (it reads infinity)
         const bool direct = enqueue_sort_accumulate<F>(D, st, P, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo,
-                                                       D.scalars.as<Fr>() + lo, cnt, j == 0, j > 0 || want_direct, want_direct);
+                                                       D.scalars.as<Fr>() + lo, cnt, j == 0, j > 0 || want_direct, want_direct,
+                                                       overlap ? D.sort_stream : (cudaStream_t) nullptr, D.ev_sorted[set]);
         enqueue_fold<F>(D, st, P, j == 0 && !want_direct, direct);
+        if (overlap) CK(cudaEventRecord(D.ev_set_free[set], st));
     }
     enqueue_reduce<F>(D, st, P, true);
     CK(cudaEventRecord(D.ev[1], st));

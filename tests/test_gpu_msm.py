@@ -47,13 +47,16 @@ def test_pipelined_upload_chunks(engine, orc, golden, grp):
     try:
         # dense_direct = 1 (default): whole buckets go from k_accumulate straight into the array that lives across the chunks and
         # only split buckets are folded; 0: every chunk folds every bucket
-        for dense_direct, part_sort in ((1, 1), (0, 1), (1, 0)):  # (1, 0): the round-1 counting sort feeds the same lists
+        # overlap_sort = 1 (default): chunk j + 1 is sorted on a second stream (two sets of sort outputs) under the accumulation
+        # of chunk j; (1, 0, *): the round-1 counting sort feeds the same lists
+        for dense_direct, part_sort, overlap in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0), (0, 0, 0)):
             engine.set_tuning_ex("dense_direct", dense_direct)
             engine.set_tuning_ex("partition_sort", part_sort)
+            engine.set_tuning_ex("overlap_sort", overlap)
             for chunks, c, L in ((2, 0, 0), (3, 7, 4), (4, 10, 0), (7, 4, 2), (16, 12, 0)):
                 engine.set_tuning(c, L)
                 engine.set_pipeline_chunks(chunks)
-                assert (engine.multi_exp(grp, P, s) == want).all(), (grp, chunks, c, L, dense_direct)
+                assert (engine.multi_exp(grp, P, s) == want).all(), (grp, chunks, c, L, dense_direct, part_sort, overlap)
                 if c == 0:
                     continue  # fixtures are small: they take the single-kernel path unless the geometry is forced
                 for name in g["names"]:
@@ -62,6 +65,7 @@ def test_pipelined_upload_chunks(engine, orc, golden, grp):
     finally:
         engine.set_tuning_ex("dense_direct", 1)
         engine.set_tuning_ex("partition_sort", 1)
+        engine.set_tuning_ex("overlap_sort", 1)
         engine.set_tuning(0, 0)
         engine.set_pipeline_chunks(0)
 
