@@ -316,7 +316,8 @@ int b200_set_tuning(int window_bits, int chunk_len);
 int b200_set_tuning_ex(const char *key, int value);
 /* Host-buffer MSMs (b200_msm_g1/g2) upload their inputs in `chunks` index chunks whose H2D copy
  * overlaps the sort + accumulation of the previous chunk (0 = auto: 1 below 2^17 points, 2 below
- * 2^19, 4 below 2^22, else 8; at most 16).  1 disables the pipeline. */
+ * 2^19, 4 below 2^22, 8 below 2^24, else 16 = the maximum).  1 disables the pipeline.  The ingest + sort of a chunk run on a
+ * second stream under the accumulation of the previous one (tuning key "overlap_sort"). */
 int b200_set_pipeline_chunks(int chunks);
 /* IMAD roofline microbenchmark on every SM of device 0; returns multiply-adds (lane-ops)
  * per second.  kind 0: the 32x32+64 multiply-add stream of the Montgomery product

@@ -473,7 +473,7 @@ inline size_t choose_chunks(size_t n)
 {
     size_t s;
     if (g_tune_chunks > 0) s = (size_t)g_tune_chunks;
-    else s = n < (1u << 17) ? 1 : n < (1u << 19) ? 2 : n < (1u << 22) ? 4 : 8;  // profiles/r4w_e2e_chunk_probe.jsonl (2^22: 13.82 -> 13.32 ms with 8)
+    else s = n < (1u << 17) ? 1 : n < (1u << 19) ? 2 : n < (1u << 22) ? 4 : n < (1u << 24) ? 8 : 16;  // profiles/r4w_e2e_chunk_probe.jsonl, r5n (2^24: 49.4 -> 46.7 ms with 16)
     return std::max<size_t>(1, std::min<size_t>(std::min<size_t>(s, MAX_CHUNKS), n));
 }
 
