@@ -234,6 +234,7 @@ extern int g_tune_g1paired;  // k_accumulate<Fq> with the mixed addition's indep
 extern int g_tune_quads;  // 1 (default): stage 2 of the window reduction with quad-cooperative additions (k_reduce_bits_quad); 0: one thread per partial sum
 extern int g_tune_dense_direct;  // 1 (default): in pipelined MSMs k_accumulate writes single-task buckets straight into the dense array; 0: every chunk folds all buckets
 extern int g_tune_overlap_sort;  // 1 (default): pipelined MSMs sort the next chunk on a second stream while the current one is accumulated
+extern int g_tune_pinned_chunks;  // upload chunks of the host scalars of a resident-key MSM: 0 = auto (1 below 2^18, 2 below 2^21, else 4)
 extern int g_tune_g2pair;  // 1: G2 accumulation with two lanes per task (measured 5 % slower: profiles/r2n_g2_lane_pairs.jsonl); 0 (default): one thread per task
 extern int g_tune_even_chunks;  // 1 (default): equal upload chunks; 0: short first chunk (measured: no gain)
 extern int g_tune_ba;    // batch-affine tree levels in front of the XYZZ accumulation: 0 (off), 1 or 2

@@ -42,7 +42,7 @@ std::map<uint64_t, std::unique_ptr<WindowTable>> g_tables;
 uint64_t g_next_handle = 1;
 b200_stats_t g_stats;
 int g_tune_c = 0, g_tune_L = 0, g_tune_chunks = 0, g_tune_logS = -1, g_tune_split = 0, g_tune_pre = 1, g_tune_ones = 1, g_tune_host_horner = 1;
-int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 0, g_tune_even_chunks = 1, g_tune_g2blocks = 1, g_tune_red_block = 128, g_tune_g1paired = 0, g_tune_quads = 1, g_tune_dense_direct = 1, g_tune_overlap_sort = 1;
+int g_tune_sort = 1, g_tune_marginals = 0, g_tune_ba = 0, g_tune_g2pair = 0, g_tune_even_chunks = 1, g_tune_g2blocks = 1, g_tune_red_block = 128, g_tune_g1paired = 0, g_tune_quads = 1, g_tune_dense_direct = 1, g_tune_overlap_sort = 1, g_tune_pinned_chunks = 0;
 bool g_scalars_resident = false;
 
 static std::map<int, std::unique_ptr<Stager>> g_stagers;  // by CUDA device ordinal
@@ -200,6 +200,7 @@ static int apply_tuning(const std::string &k, int value)
     else if (k == "reduce_marginals") g_tune_marginals = value;  // 0: bit decomposition over all segments (round 1)
     else if (k == "batch_affine") g_tune_ba = std::min(std::max(value, 0), 2);  // tree levels of affine pair additions before the XYZZ tail
     else if (k == "reduce_block") g_tune_red_block = value;  // threads per block of k_reduce_segments
+    else if (k == "pinned_chunks") g_tune_pinned_chunks = value;  // upload chunks of a resident-key MSM's host scalars (0 = auto, 1 = one upload)
     else if (k == "overlap_sort") g_tune_overlap_sort = value;  // 0: pipelined MSMs sort and accumulate every chunk on one stream
     else if (k == "dense_direct") g_tune_dense_direct = value;  // 0: pipelined MSMs fold every bucket after every chunk
     else if (k == "reduce_quads") g_tune_quads = value;       // 0: one thread per partial sum in stage 2 of the window reduction (k_reduce_bits)

@@ -220,7 +220,7 @@ MsmPlan plan_msm(Device &D, cudaStream_t st, size_t n, size_t chunk_max, bool de
         P.split = std::min(P.split, 64u);
     }
     if (g_tune_split > 0) P.split = (uint32_t)std::min(g_tune_split, 64);
-    if (g.Wb == 1 && !dense && g_tune_host_horner) {  // one window: per-job sums to the host (MsmGeom::red_jobs)
+    if (g.Wb == 1 && g_tune_host_horner) {  // one window: per-job sums to the host (MsmGeom::red_jobs); also from the dense array of a chunked call
         P.g.red_jobs = P.njobs;
         P.g.red_logS = P.logS;
         uint32_t lgM = 0;
@@ -490,6 +490,44 @@ inline std::vector<std::pair<size_t, size_t>> pipeline_ranges(size_t n, size_t S
     return r;
 }
 
+// The chunk loop of a pipelined MSM: chunk j's inputs are uploaded on the copy stream, ingested (host bases) and sorted on the
+// sort stream, accumulated into the dense per-bucket array on `st`.  d_aff / d_flags / d_scalars are the device arrays of the
+// WHOLE shard; for a precomputed key d_aff is the table and the chunk's offset goes into the geometry (MsmGeom::pre_off).
+template <class F, class Upload>
+void enqueue_chunks(Device &D, cudaStream_t st, const MsmPlan &P, const std::vector<std::pair<size_t, size_t>> &ranges, const Upload &upload,
+                    bool ingest, const Affine<F> *d_aff, const uint8_t *d_flags, const Fr *d_scalars)
+{
+    // the dense per-bucket sums: k_accumulate writes whole buckets into it directly (knob dense_direct), so it starts out as
+    // all infinity (= all zero bytes) instead of being initialised by the first fold
+    const bool want_direct = g_tune_dense_direct != 0;
+    if (want_direct) CK(cudaMemsetAsync(D.bucket_sum.p, 0, (size_t)P.g.NB * sizeof(XYZZ<F>), st));
+    // ingest + sort of chunk j + 1 on the sort stream under the accumulation of chunk j: the sort kernels wait on memory and
+    // shared-memory atomics, the accumulation on the multiply-add pipe.  The batch-affine and lane-pair options share scratch
+    // with the ingest and keep everything on one stream.
+    const bool overlap = g_tune_overlap_sort && !g_tune_ba && !(sizeof(F) == 64 && g_tune_g2pair);
+    if (overlap) CK(cudaStreamWaitEvent(D.sort_stream, D.ev_sync, 0));
+    for (size_t j = 0; j < ranges.size(); j++) {
+        const size_t lo = ranges[j].first, cnt = ranges[j].second;
+        const int set = (int)(j & 1);
+        if (overlap && j > 0) D.swap_sort_set();
+        cudaStream_t pre = overlap ? D.sort_stream : st;
+        upload(D.copy_stream, lo, cnt);
+        CK(cudaEventRecord(D.ev_ready[j], D.copy_stream));
+        CK(cudaStreamWaitEvent(pre, D.ev_ready[j], 0));
+        if (overlap && j >= 2) CK(cudaStreamWaitEvent(pre, D.ev_set_free[set], 0));  // chunk j - 2 read this set
+        if (ingest)
+            run_ingest<F, false>(D, pre, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
+        MsmPlan Pj = P;
+        if (P.g.pre_stride) Pj.g.pre_off = P.g.pre_off + (uint32_t)lo;  // level k of the table: k * pre_stride + pre_off + i
+        // with the array cleared, chunk 0 can be "seeded" like the others (it reads infinity)
+        const bool direct = enqueue_sort_accumulate<F>(D, st, Pj, P.g.pre_stride ? d_aff : d_aff + lo, d_flags + lo, d_scalars + lo, cnt, j == 0,
+                                                       j > 0 || want_direct, want_direct, overlap ? D.sort_stream : (cudaStream_t) nullptr,
+                                                       D.ev_sorted[set]);
+        enqueue_fold<F>(D, st, P, j == 0 && !want_direct, direct);
+        if (overlap) CK(cudaEventRecord(D.ev_set_free[set], st));
+    }
+}
+
 template <class F>
 MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *scalars, size_t n)
 {
@@ -518,32 +556,41 @@ MsmGeom enqueue_msm_from_host(Device &D, const uint64_t *bases, const uint64_t *
     // order the copy stream after whatever the compute stream still has in flight on these buffers
     CK(cudaEventRecord(D.ev_sync, st));
     CK(cudaStreamWaitEvent(D.copy_stream, D.ev_sync, 0));
-    // the dense per-bucket sums: k_accumulate writes whole buckets into it directly (knob dense_direct), so it starts out as
-    // all infinity (= all zero bytes) instead of being initialised by the first fold
-    const bool want_direct = g_tune_dense_direct != 0;
-    if (want_direct) CK(cudaMemsetAsync(D.bucket_sum.p, 0, (size_t)P.g.NB * sizeof(XYZZ<F>), st));
-    // ingest + sort of chunk j + 1 on the sort stream under the accumulation of chunk j: the sort kernels wait on memory and
-    // shared-memory atomics, the accumulation on the multiply-add pipe.  The batch-affine and lane-pair options share scratch
-    // with the ingest and keep everything on one stream.
-    const bool overlap = g_tune_overlap_sort && !g_tune_ba && !(sizeof(F) == 64 && g_tune_g2pair);
-    if (overlap) CK(cudaStreamWaitEvent(D.sort_stream, D.ev_sync, 0));
-    for (size_t j = 0; j < ranges.size(); j++) {
-        const size_t lo = ranges[j].first, cnt = ranges[j].second;
-        const int set = (int)(j & 1);
-        if (overlap && j > 0) D.swap_sort_set();
-        cudaStream_t pre = overlap ? D.sort_stream : st;
-        upload(D.copy_stream, lo, cnt);
-        CK(cudaEventRecord(D.ev_ready[j], D.copy_stream));
-        CK(cudaStreamWaitEvent(pre, D.ev_ready[j], 0));
-        if (overlap && j >= 2) CK(cudaStreamWaitEvent(pre, D.ev_set_free[set], 0));  // chunk j - 2 read this set
-        run_ingest<F, false>(D, pre, D.bases_jac.as<Jacobian<F>>() + lo, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo, cnt);
-        // with the array cleared, chunk 0 can be "seeded" like the others (it reads infinity)
-        const bool direct = enqueue_sort_accumulate<F>(D, st, P, D.bases_aff.as<Affine<F>>() + lo, D.flags.as<uint8_t>() + lo,
-                                                       D.scalars.as<Fr>() + lo, cnt, j == 0, j > 0 || want_direct, want_direct,
-                                                       overlap ? D.sort_stream : (cudaStream_t) nullptr, D.ev_sorted[set]);
-        enqueue_fold<F>(D, st, P, j == 0 && !want_direct, direct);
-        if (overlap) CK(cudaEventRecord(D.ev_set_free[set], st));
+    enqueue_chunks<F>(D, st, P, ranges, upload, /*ingest=*/true, D.bases_aff.as<Affine<F>>(), D.flags.as<uint8_t>(), D.scalars.as<Fr>());
+    enqueue_reduce<F>(D, st, P, true);
+    CK(cudaEventRecord(D.ev[1], st));
+    return P.g;
+}
+
+// Resident key, HOST scalars (a commitment under a fixed key: CommScheme::commit, LS/prototools/commit.h): the 32 B per point
+// of scalars are the only upload, but at 2^20 they still take 0.6 ms in front of a 2.7 ms pipeline.  From 2^18 points on the
+// scalars arrive in two (from 2^21: four) index chunks through the same chunk loop as the cold-key call: chunk 1 is uploaded and
+// sorted under the accumulation of chunk 0.  `forced`: the precomputed-key geometry (d_aff is then the level table).
+inline size_t choose_scalar_chunks(size_t n)
+{
+    if (g_tune_pinned_chunks > 0) return std::min<size_t>((size_t)g_tune_pinned_chunks, std::min<size_t>(MAX_CHUNKS, n));
+    return n < (1u << 18) ? 1 : n < (1u << 21) ? 2 : 4;  // profiles/r5q_resident_scalar_chunks.jsonl
+}
+
+template <class F>
+MsmGeom enqueue_msm_host_scalars(Device &D, cudaStream_t st, const Affine<F> *d_aff, const uint8_t *d_flags, const uint64_t *scalars, size_t n,
+                                 const MsmGeom *forced = nullptr)
+{
+    const size_t S = st == D.stream ? choose_scalar_chunks(n) : 1;
+    D.scalars.ensure(n * sizeof(Fr));
+    if (S == 1) {
+        h2d(D, D.scalars.p, scalars, n * sizeof(Fr), st);
+        return enqueue_msm<F>(D, st, d_aff, d_flags, D.scalars.as<Fr>(), n, forced);
     }
+    const auto upload = [&](cudaStream_t cs, size_t lo, size_t cnt) { h2d(D, D.scalars.as<Fr>() + lo, scalars + lo * 4, cnt * sizeof(Fr), cs); };
+    const auto ranges = split_range(n, S);
+    size_t chunk_max = 0;
+    for (auto &r : ranges) chunk_max = std::max(chunk_max, r.second);
+    const MsmPlan P = plan_msm<F>(D, st, n, chunk_max, true, forced);
+    CK(cudaEventRecord(D.ev[0], st));
+    CK(cudaEventRecord(D.ev_sync, st));
+    CK(cudaStreamWaitEvent(D.copy_stream, D.ev_sync, 0));
+    enqueue_chunks<F>(D, st, P, ranges, upload, /*ingest=*/false, d_aff, d_flags, (const Fr *)D.scalars.as<Fr>());
     enqueue_reduce<F>(D, st, P, true);
     CK(cudaEventRecord(D.ev[1], st));
     return P.g;
@@ -899,13 +946,16 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
             CK(cudaSetDevice(D.id));
             cudaStream_t st = (d_scalars && stream) ? (cudaStream_t)stream : D.stream;
             engine_enter(D, st);
-            const Fr *ds;
+            const Fr *ds = nullptr;
+            const uint64_t *hs = nullptr;  // host scalars of a piece that takes the multi-kernel pipeline: uploaded in chunks
             if (d_scalars) {
                 ds = reinterpret_cast<const Fr *>(d_scalars);
-            } else {
+            } else if (P.cnt <= SMALL_MAX_N && g_tune_c == 0) {
                 D.scalars.ensure(P.cnt * sizeof(Fr));
                 h2d(D, D.scalars.p, scalars + (P.lo - offset) * 4, P.cnt * sizeof(Fr), st);
                 ds = D.scalars.as<Fr>();
+            } else {
+                hs = scalars + (P.lo - offset) * 4;
             }
             const Affine<F> *aff = reinterpret_cast<const Affine<F> *>(S.d_aff) + (P.lo - S.begin);
             if (P.cnt <= SMALL_MAX_N && g_tune_c == 0) {
@@ -938,8 +988,14 @@ int msm_pinned(uint64_t handle, size_t offset, const uint64_t *scalars, const vo
             if (pre && g_tune_pre != 2) pre = precomputed_pays(P.cnt, S.pre_c);  // 2 = always (tests)
             if (pre) {
                 const MsmGeom gp = choose_geometry(P.cnt, S.pre_c, (uint32_t)S.count, (uint32_t)(P.lo - S.begin), sizeof(F) == 64);
-                geoms[pi] = enqueue_msm<F>(D, st, reinterpret_cast<const Affine<F> *>(S.d_pre), S.d_flags + (P.lo - S.begin), ds,
-                                           P.cnt, &gp);
+                if (hs)
+                    geoms[pi] = enqueue_msm_host_scalars<F>(D, st, reinterpret_cast<const Affine<F> *>(S.d_pre), S.d_flags + (P.lo - S.begin), hs,
+                                                            P.cnt, &gp);
+                else
+                    geoms[pi] = enqueue_msm<F>(D, st, reinterpret_cast<const Affine<F> *>(S.d_pre), S.d_flags + (P.lo - S.begin), ds,
+                                               P.cnt, &gp);
+            } else if (hs) {
+                geoms[pi] = enqueue_msm_host_scalars<F>(D, st, aff, S.d_flags + (P.lo - S.begin), hs, P.cnt);
             } else {
                 geoms[pi] = enqueue_msm<F>(D, st, aff, S.d_flags + (P.lo - S.begin), ds, P.cnt);
             }

@@ -158,6 +158,41 @@ def test_precomputed_key(engine, orc, golden, grp, n):
         key.close()
 
 
+@pytest.mark.parametrize("grp,n", [("g1", 7001), ("g2", 4600)])
+def test_resident_key_chunked_scalars(engine, orc, grp, n):
+    """A commitment under a resident key with HOST scalars uploads them in index chunks from 2^19 points on (chunk j + 1 is
+    uploaded and sorted under the accumulation of chunk j; `pinned_chunks` forces the chunk count here): plain and precomputed
+    keys, sub-ranges at an offset, zero / repeated / opposite bases, skewed scalars (the ones filter across chunks), the
+    per-job host Horner from the dense array and the device-side weighting."""
+    P, _ = inputs.bases(orc, grp, n, seed=881, affine=False)
+    P[5] = inputs.zero_point(grp)
+    P[7] = P[6]
+    P[9] = inputs.negate(orc, grp, P[8:9])[0]
+    key = engine.CommitmentKey(grp, P)
+    try:
+        for pre_c in (0, 6, 11):
+            if pre_c:
+                key.precompute(pre_c)
+                engine.set_tuning_ex("use_precomputed", 2)
+            for chunks in (2, 3, 5):
+                engine.set_tuning_ex("pinned_chunks", chunks)
+                for m, off in ((n, 0), (n - 3, 2), (4200, 311)):
+                    for s in (inputs.fr_uniform(orc, m, seed=882 + m), inputs.fr_zero_one_heavy(orc, m, seed=883)):
+                        s[3:12] = s[3]
+                        want = orc.msm(grp, P[off:off + m], s, chunks=orc.max_threads(), variant=1)
+                        assert (key.multi_exp(s, offset=off) == want).all(), (grp, pre_c, chunks, m, off)
+                        if pre_c:
+                            engine.set_tuning_ex("host_horner", 0)
+                            try:
+                                assert (key.multi_exp(s, offset=off) == want).all(), (grp, pre_c, chunks, m, off, "device horner")
+                            finally:
+                                engine.set_tuning_ex("host_horner", 1)
+    finally:
+        engine.set_tuning_ex("pinned_chunks", 0)
+        engine.set_tuning_ex("use_precomputed", 1)
+        key.close()
+
+
 @pytest.mark.parametrize("grp,n", [("g1", 9000), ("g2", 5000)])
 def test_ones_filter(engine, orc, grp, n):
     """Scalars equal to one are summed directly (multi_exp_with_mixed_addition's special addition,
