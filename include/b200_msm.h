@@ -310,7 +310,9 @@ int b200_set_tuning(int window_bits, int chunk_len);
  * "reduce_quads" (1 / 0: one thread per partial sum in stage 2 of the window reduction), "reduce_marginals" (0 / 1),
  * "reduce_block" (128 / 32..96 threads per block in stage 1), "dense_direct" (1 / 0: pipelined MSMs fold every bucket after
  * every chunk), "batch_affine" (0 / 1, 2 tree levels of affine pair additions), "g2_lane_pairs" (0 / 1), "g2_blocks" (1 / 2, 3:
- * register budgets of the G2 accumulation), "g1_paired" (0 / 1), "even_chunks" (1 / 0).  DESIGN.md section 4 has the numbers.
+ * register budgets of the G2 accumulation), "g1_paired" (0 / 1), "even_chunks" (1 / 0), "overlap_sort" (1 / 0: chunked calls
+ * sort and accumulate on one stream), "pinned_chunks" (0 = auto / n: upload chunks of a resident-key MSM's host scalars).
+ * DESIGN.md sections 4 and 6 have the numbers.
  * The same keys can be set for a whole process with B200_TUNE="key=value,key=value"; B200_TRACE=1 prints one stderr line per
  * call (wall time, sizes, transfers) and every host stall above 1 ms inside it. */
 int b200_set_tuning_ex(const char *key, int value);
