@@ -43,6 +43,44 @@ int emu_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t
     return 0;
 }
 
+// The paired forms (field.cuh: Fp::mul2, Fp::mul_add2; curve.cuh: xyzz_madd_paired), measured options of the engine:
+// which 0: (a b, c d) by mul2; 1: (a b + c d, a d + c b) by mul_add2.  field: 0 Fq, 1 Fr.
+int emu_pair_field_op(int field, int which, const uint64_t *a, const uint64_t *b, const uint64_t *c, const uint64_t *d, size_t n,
+                      uint64_t *out0, uint64_t *out1)
+{
+    for (size_t i = 0; i < n; i++) {
+        if (field == 0) {
+            const Fq A = ld<Fq>(a + 4 * i), B = ld<Fq>(b + 4 * i), C = ld<Fq>(c + 4 * i), D = ld<Fq>(d + 4 * i);
+            Fq r0, r1;
+            if (which == 0) Fq::mul2(r0, r1, A, B, C, D);
+            else Fq::mul_add2(r0, r1, A, B, C, D, A, D, C, B);
+            st(out0 + 4 * i, r0);
+            st(out1 + 4 * i, r1);
+        } else {
+            const Fr A = ld<Fr>(a + 4 * i), B = ld<Fr>(b + 4 * i), C = ld<Fr>(c + 4 * i), D = ld<Fr>(d + 4 * i);
+            Fr r0, r1;
+            if (which == 0) Fr::mul2(r0, r1, A, B, C, D);
+            else Fr::mul_add2(r0, r1, A, B, C, D, A, D, C, B);
+            st(out0 + 4 * i, r0);
+            st(out1 + 4 * i, r1);
+        }
+    }
+    return 0;
+}
+
+// a (Jacobian) + affine(b) (negated when neg != 0) through xyzz_madd_paired; b must have Z == 1 or be zero (G1 only)
+int emu_madd_paired_g1(const uint64_t *a, const uint64_t *b, size_t n, int neg, uint64_t *out)
+{
+    typedef Jacobian<Fq> J;
+    for (size_t i = 0; i < n; i++) {
+        XYZZ<Fq> acc = XYZZ<Fq>::from_jacobian(ld<J>(a + 12 * i));
+        const J q = ld<J>(b + 12 * i);
+        if (!q.is_inf()) xyzz_madd_paired(acc, q.x, q.y, neg != 0);
+        st(out + 12 * i, acc.to_jacobian());
+    }
+    return 0;
+}
+
 // group: 0 G1, 1 G2
 int emu_group_op(int group, int op, const uint64_t *a, const uint64_t *b, size_t n, uint32_t k, uint64_t *out)
 {

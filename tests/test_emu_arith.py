@@ -105,3 +105,43 @@ def test_group_formulas(emu, orc, golden, gi, grp):
     for k in (0, 1, 2, 3, 5, 16, 255, 32767, 40000):
         want = orc.scalar_mul(grp, P, np.tile(ints_to_mont([k], R_ORDER), (P.shape[0], 1)), stride_base=True)
         assert (norm(group_op(emu, gi, 7, P, None, k)) == want).all(), k
+
+
+@pytest.mark.parametrize("field,mod,name", [(0, Q, "fq"), (1, R_ORDER, "fr")])
+def test_paired_products(emu, orc, field, mod, name):
+    """Fp::mul2 (two independent Montgomery products with alternating rows) and Fp::mul_add2 (two fused two-product passes
+    with alternating rows): measured options of the accumulation kernels; same limbs as the plain forms."""
+    rng = np.random.default_rng(21 + field)
+    n = 2000
+    a, b, c, d = (ints_to_mont(edge_and_random(rng, n, mod), mod) for _ in range(4))
+    b, d = b[::-1].copy(), d[::-1].copy()
+    a[:10] = np.array([int_to_limbs(v) for v in edge_and_random(rng, 10, mod)])  # raw residues are valid images too
+    out0, out1 = np.zeros_like(a), np.zeros_like(a)
+    args = lambda: (_p(a), _p(b), _p(c), _p(d), ctypes.c_size_t(n), _p(out0), _p(out1))
+    assert emu.emu_pair_field_op(field, 0, *args()) == 0
+    assert (out0 == orc.field_op(name, 0, a, b)).all() and (out1 == orc.field_op(name, 0, c, d)).all()
+    assert emu.emu_pair_field_op(field, 1, *args()) == 0
+    want0 = orc.field_op(name, 2, orc.field_op(name, 0, a, b), orc.field_op(name, 0, c, d))
+    want1 = orc.field_op(name, 2, orc.field_op(name, 0, a, d), orc.field_op(name, 0, c, b))
+    assert (out0 == want0).all() and (out1 == want1).all()
+
+
+def test_paired_mixed_addition(emu, orc, golden):
+    """xyzz_madd_paired (the mixed addition with its independent products issued in pairs, knob g1_paired) on the reference
+    fixtures, including the same-point (tangent) and opposite-point rows they contain."""
+    g = golden("group_g1")
+    P, Qa = g["P"], g["Q_affine"]
+    norm = lambda x: orc.group_op("g1", 3, x)
+    out = np.zeros_like(P)
+    assert emu.emu_madd_paired_g1(_p(np.ascontiguousarray(P)), _p(np.ascontiguousarray(Qa)), ctypes.c_size_t(P.shape[0]), 0, _p(out)) == 0
+    assert (norm(out) == norm(g["mixed_add"])).all()
+    negQ = orc.group_op("g1", 4, Qa)
+    assert emu.emu_madd_paired_g1(_p(np.ascontiguousarray(P)), _p(np.ascontiguousarray(Qa)), ctypes.c_size_t(P.shape[0]), 1, _p(out)) == 0
+    assert (norm(out) == norm(orc.group_op("g1", 1, P, negQ))).all()
+    # P + P (tangent branch) and P - P (infinity) through the paired adder
+    Pa = norm(P)
+    assert emu.emu_madd_paired_g1(_p(np.ascontiguousarray(Pa)), _p(np.ascontiguousarray(Pa)), ctypes.c_size_t(Pa.shape[0]), 0, _p(out)) == 0
+    assert (norm(out) == norm(orc.group_op("g1", 2, Pa))).all()
+    assert emu.emu_madd_paired_g1(_p(np.ascontiguousarray(Pa)), _p(np.ascontiguousarray(Pa)), ctypes.c_size_t(Pa.shape[0]), 1, _p(out)) == 0
+    zero = norm(out)
+    assert (zero[:, 8:12] == 0).all()  # Z == 0: the point at infinity
